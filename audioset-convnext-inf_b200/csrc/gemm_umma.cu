@@ -1,0 +1,326 @@
+// tcgen05 GEMM:  out[M,N] (bf16) = epi( A[M,K] (bf16) . W[N,K]^T (bf16) ), fp32 accumulation in TMEM.
+//
+// Persistent, warp-specialised, one CTA per SM:
+//   warp 0      TMA producer   (cp.async.bulk.tensor, 128B-swizzled 128x64 / BNx64 tiles)
+//   warp 1      MMA issuer     (one elected thread, tcgen05.mma.cta_group::1.kind::f16, M=128, N=BN, K=16)
+//   warp 2      TMEM allocator
+//   warps 4..   epilogue       (tcgen05.ld 32x32b -> bias / GELU / layer-scale+residual -> bf16 -> global)
+// Pipelines: smem ring (full/empty mbarriers, STAGES deep) between TMA and MMA; two TMEM accumulators
+// (tmem_full/tmem_empty) between MMA and epilogue, so tile i's epilogue overlaps tile i+1's MMAs.
+//
+// Used for pwconv1+GELU / pwconv2+gamma+residual (reference convnext.py:79-86) and the 2x2/s2 downsample
+// convolutions as GEMMs over the patch matrix (convnext.py:231-234).
+#include "common.cuh"
+#include "ptx.cuh"
+#include "tmap.cuh"
+
+namespace acx {
+
+struct GemmArgs {
+  bf16* out;
+  const float* bias;
+  const float* gamma;
+  const bf16* resid;
+  int M, N, K;
+};
+
+// GELU for the bf16 tensor-core path: 0.5 x (1 + tanh(x (a + b x^2 + c x^4))) with MUFU.TANH.  (a, b, c)
+// are a minimax re-fit against the EXACT erf GELU the reference uses (nn.GELU(), convnext.py:65):
+// max |err| = 2.6e-5 over all x (textbook tanh-GELU: 4.7e-4), ~10x below the bf16 rounding applied to
+// the result.  x^2 is clamped at 50 (tanh already saturated) so the negative x^4 term cannot flip the
+// sign for |x| > 11.  Checked on the CPU by tests/test_host_logic.py::test_gelu_fit.
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float x2 = fminf(x * x, 50.0f);
+  const float inner = x * fmaf(x2, fmaf(x2, -3.51516788e-04f, 3.70056460e-02f), 7.97507884e-01f);
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(inner));
+  const float hx = 0.5f * x;
+  return fmaf(hx, t, hx);
+}
+
+template <int BN_, int NEPI_>
+struct GemmCfg {
+  static constexpr int BM = 128, BN = BN_, BK = 64, NEPI = NEPI_;
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES_RAW = (196 * 1024) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  static constexpr int ACC_STRIDE = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+  static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
+  static constexpr int NGROUPS = NEPI / 4;             // column groups sharing a TMEM lane quadrant
+  static constexpr int COLS_PER_GROUP = BN / NGROUPS;
+  static constexpr int CHUNK = (COLS_PER_GROUP % 32 == 0) ? 32 : 16;
+  static constexpr int THREADS = 128 + 32 * NEPI;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N constraint for M=128");
+  static_assert(COLS_PER_GROUP % CHUNK == 0, "epilogue column split");
+  static_assert(B_BYTES % 1024 == 0, "stage buffers must stay 1024B aligned for SWIZZLE_128B");
+};
+
+template <int CHUNK>
+__device__ __forceinline__ void tmem_ld_chunk(uint32_t taddr, uint32_t (&r)[CHUNK]);
+template <>
+__device__ __forceinline__ void tmem_ld_chunk<32>(uint32_t taddr, uint32_t (&r)[32]) {
+  ptx::tmem_ld_32x32b_x32(taddr, r);
+}
+template <>
+__device__ __forceinline__ void tmem_ld_chunk<16>(uint32_t taddr, uint32_t (&r)[16]) {
+  ptx::tmem_ld_32x32b_x16(taddr, r);
+}
+
+template <int BN, int EPI, int NEPI>
+__global__ void __launch_bounds__(GemmCfg<BN, NEPI>::THREADS, 1)
+    umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmArgs g) {
+  using Cfg = GemmCfg<BN, NEPI>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + Cfg::STAGES;
+  uint64_t* tfull_bar = empty_bar + Cfg::STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && ptx::elect_one()) {
+    ptx::prefetch_tensormap(&tmA);
+    ptx::prefetch_tensormap(&tmB);
+  }
+  if (warp == 1 && ptx::elect_one()) {
+    for (int s = 0; s < Cfg::STAGES; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(&tfull_bar[a], 1);
+      ptx::mbar_init(&tempty_bar[a], NEPI);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_m_tiles = (g.M + Cfg::BM - 1) / Cfg::BM;
+  const int num_n_tiles = g.N / BN;
+  const int num_tiles = num_m_tiles * num_n_tiles;
+  const int num_kb = (g.K + Cfg::BK - 1) / Cfg::BK;
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (ptx::elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / num_n_tiles) * Cfg::BM;
+        const int n0 = (tile % num_n_tiles) * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+          uint8_t* sb = sa + Cfg::A_BYTES;
+          ptx::mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          ptx::tma_load_2d(sa, &tmA, &full_bar[stage], kb * Cfg::BK, m0);
+          ptx::tma_load_2d(sb, &tmB, &full_bar[stage], kb * Cfg::BK, n0);
+          if (++stage == Cfg::STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ==================================
+    if (ptx::elect_one()) {
+      constexpr uint32_t idesc = ptx::umma_idesc_bf16(Cfg::BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * Cfg::ACC_STRIDE;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          ptx::mbar_wait(&full_bar[stage], phase);
+          ptx::tc_fence_after();
+          const uint32_t sa = ptx::smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint64_t da = ptx::umma_desc_sw128_kmajor(sa);
+          const uint64_t db = ptx::umma_desc_sw128_kmajor(sa + Cfg::A_BYTES);
+#pragma unroll
+          for (int k = 0; k < Cfg::BK / 16; ++k) {
+            if (kb * Cfg::BK + k * 16 < g.K) {
+              // advance 16 bf16 = 32 B along K inside the 128B swizzle row: +2 in the (addr >> 4) field
+              ptx::umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+          }
+          ptx::umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
+          if (++stage == Cfg::STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        ptx::umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+      }
+    }
+  } else if (warp >= 4) {
+    // ================================ epilogue =====================================
+    const int ew = warp - 4;
+    const int quad = warp & 3;            // TMEM lane quadrant this warp may access
+    const int group = ew >> 2;            // column group
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int m0 = (tile / num_n_tiles) * Cfg::BM;
+      const int n0 = (tile % num_n_tiles) * BN;
+      const int row = m0 + quad * 32 + lane;
+      const bool row_ok = row < g.M;
+      ptx::mbar_wait(&tfull_bar[acc], acc_phase);
+      ptx::tc_fence_after();
+      const uint32_t t_base = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * Cfg::ACC_STRIDE;
+#pragma unroll 1
+      for (int c0 = group * Cfg::COLS_PER_GROUP; c0 < (group + 1) * Cfg::COLS_PER_GROUP; c0 += Cfg::CHUNK) {
+        uint32_t r[Cfg::CHUNK];
+        tmem_ld_chunk<Cfg::CHUNK>(t_base + c0, r);
+        ptx::tmem_ld_wait();
+        const int n = n0 + c0;
+        float v[Cfg::CHUNK];
+#pragma unroll
+        for (int j = 0; j < Cfg::CHUNK; j += 4) {
+          const float4 b4 = __ldg(reinterpret_cast<const float4*>(g.bias + n + j));
+          v[j + 0] = __uint_as_float(r[j + 0]) + b4.x;
+          v[j + 1] = __uint_as_float(r[j + 1]) + b4.y;
+          v[j + 2] = __uint_as_float(r[j + 2]) + b4.z;
+          v[j + 3] = __uint_as_float(r[j + 3]) + b4.w;
+        }
+        if (EPI == ACX_EPI_BIAS_GELU) {
+#pragma unroll
+          for (int j = 0; j < Cfg::CHUNK; ++j) v[j] = gelu_fast(v[j]);
+        }
+        if (EPI == ACX_EPI_BIAS_SCALE_RESID) {
+          if (row_ok) {
+            const uint4* rp = reinterpret_cast<const uint4*>(g.resid + (size_t)row * g.N + n);
+#pragma unroll
+            for (int j = 0; j < Cfg::CHUNK; j += 8) {
+              const uint4 q = rp[j / 8];  // plain load: `out` may alias `resid` (in-place residual update)
+              const float4 g0 = __ldg(reinterpret_cast<const float4*>(g.gamma + n + j));
+              const float4 g1 = __ldg(reinterpret_cast<const float4*>(g.gamma + n + j + 4));
+              float2 f;
+              f = Pair<bf16>::unpack(q.x); v[j + 0] = fmaf(g0.x, v[j + 0], f.x); v[j + 1] = fmaf(g0.y, v[j + 1], f.y);
+              f = Pair<bf16>::unpack(q.y); v[j + 2] = fmaf(g0.z, v[j + 2], f.x); v[j + 3] = fmaf(g0.w, v[j + 3], f.y);
+              f = Pair<bf16>::unpack(q.z); v[j + 4] = fmaf(g1.x, v[j + 4], f.x); v[j + 5] = fmaf(g1.y, v[j + 5], f.y);
+              f = Pair<bf16>::unpack(q.w); v[j + 6] = fmaf(g1.z, v[j + 6], f.x); v[j + 7] = fmaf(g1.w, v[j + 7], f.y);
+            }
+          }
+        }
+        if (row_ok) {
+          uint4* op = reinterpret_cast<uint4*>(g.out + (size_t)row * g.N + n);
+#pragma unroll
+          for (int j = 0; j < Cfg::CHUNK; j += 8) {
+            uint4 q;
+            q.x = Pair<bf16>::pack(v[j + 0], v[j + 1]);
+            q.y = Pair<bf16>::pack(v[j + 2], v[j + 3]);
+            q.z = Pair<bf16>::pack(v[j + 4], v[j + 5]);
+            q.w = Pair<bf16>::pack(v[j + 6], v[j + 7]);
+            op[j / 8] = q;
+          }
+        }
+      }
+      // all TMEM reads of this accumulator are complete (wait::ld above): hand it back to the MMA warp
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+template <int BN, int EPI, int NEPI>
+static int launch_umma_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& g, cudaStream_t st) {
+  using Cfg = GemmCfg<BN, NEPI>;
+  auto kern = umma_gemm_kernel<BN, EPI, NEPI>;
+  static bool configured = false;  // per-instantiation; benign race (idempotent attribute set)
+  if (!configured) {
+    ACX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    configured = true;
+  }
+  int dev = 0, sms = 0;
+  ACX_CUDA(cudaGetDevice(&dev));
+  ACX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int tiles = ceil_div(g.M, Cfg::BM) * (g.N / BN);
+  const int grid = tiles < sms ? tiles : sms;
+  kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, g);
+  ACX_CUDA(cudaGetLastError());
+  return ACX_OK;
+}
+
+template <int EPI>
+static int dispatch_bn(const CUtensorMap& tmA, const void* W, const GemmArgs& g, cudaStream_t st) {
+  // tile-N choice: the largest supported BN that divides N (fewer A re-reads, longer MMAs)
+  int bn = 0;
+  for (int cand : {256, 192, 128, 96}) {
+    if (g.N % cand == 0) {
+      bn = cand;
+      break;
+    }
+  }
+  ACX_CHECK(bn != 0, ACX_ERR_UNSUPPORTED, "gemm_bf16: N=%d is not a multiple of 96/128/192/256", g.N);
+  CUtensorMap tmB;
+  int rc = make_tmap_2d_bf16(&tmB, W, (uint64_t)g.K, (uint64_t)g.N, (uint64_t)g.K * 2, 64, (uint32_t)bn);
+  if (rc != ACX_OK) return rc;
+  switch (bn) {
+    case 256: return launch_umma_gemm<256, EPI, 8>(tmA, tmB, g, st);
+    case 192: return launch_umma_gemm<192, EPI, 8>(tmA, tmB, g, st);
+    case 128: return launch_umma_gemm<128, EPI, 8>(tmA, tmB, g, st);
+    default:  return launch_umma_gemm<96, EPI, 8>(tmA, tmB, g, st);
+  }
+}
+
+}  // namespace acx
+
+using namespace acx;
+
+extern "C" int acx_gemm_bf16(const void* A, const void* W, void* out, int M, int N, int K, int epilogue,
+                             const float* bias, const float* gamma, const void* resid, void* stream) {
+  ACX_CHECK(A && W && out && bias, ACX_ERR_ARG, "gemm_bf16: null pointer (A, W, out and bias are required)");
+  ACX_CHECK(M > 0 && N > 0 && K > 0 && K % 8 == 0, ACX_ERR_ARG, "gemm_bf16: K=%d must be a positive multiple of 8", K);
+  ACX_CHECK((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0 &&
+                (reinterpret_cast<uintptr_t>(out) & 15) == 0,
+            ACX_ERR_ARG, "gemm_bf16: A, W and out must be 16-byte aligned");
+  if (epilogue == ACX_EPI_BIAS_SCALE_RESID)
+    ACX_CHECK(gamma && resid, ACX_ERR_ARG, "gemm_bf16: scale+residual epilogue needs gamma and resid");
+  GemmArgs g;
+  g.out = reinterpret_cast<bf16*>(out);
+  g.bias = bias;
+  g.gamma = gamma;
+  g.resid = reinterpret_cast<const bf16*>(resid);
+  g.M = M;
+  g.N = N;
+  g.K = K;
+  CUtensorMap tmA;
+  int rc = make_tmap_2d_bf16(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)K * 2, 64, 128);
+  if (rc != ACX_OK) return rc;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  switch (epilogue) {
+    case ACX_EPI_BIAS: return dispatch_bn<ACX_EPI_BIAS>(tmA, W, g, st);
+    case ACX_EPI_BIAS_GELU: return dispatch_bn<ACX_EPI_BIAS_GELU>(tmA, W, g, st);
+    case ACX_EPI_BIAS_SCALE_RESID: return dispatch_bn<ACX_EPI_BIAS_SCALE_RESID>(tmA, W, g, st);
+    default:
+      set_error("gemm_bf16: unknown epilogue %d", epilogue);
+      return ACX_ERR_ARG;
+  }
+}

@@ -1,0 +1,564 @@
+// CUDA-core / bandwidth kernels of the hot path (channels-last, H = time, W = mel):
+//   wave_prep        reflect pad + fp32 -> bf16 hi/lo split            (torchlibrosa STFT.forward pad)
+//   power_mel_log    re^2+im^2 -> banded mel -> 10 log10 -> bn0        (fp32-accurate path)
+//   stem             4x4/s4 patchify conv + LayerNorm(96)              (CX:688-691, CX:227)
+//   dwconv_ln        depthwise 7x7 + channels-last LayerNorm           (CX:76-78)
+//   ln_patchify      channels_first LayerNorm + 2x2 patch gather       (CX:231-234)
+//   head             mel-mean, time max+mean, LayerNorm, fc, sigmoid   (CX:279-285, CX:321-325)
+//   nhwc_to_nchw     frame-embedding layout                            (CX:399-402)
+// "CX" = reference src/audioset_convnext_inf/pytorch/convnext.py.
+#include "common.cuh"
+
+namespace acx {
+
+// =============================================================================================
+// wave_prep
+// =============================================================================================
+template <bool kSplit>
+__global__ void wave_prep_kernel(const float* __restrict__ wave, void* __restrict__ hi_, void* __restrict__ lo_,
+                                 int L, int pad, int ld_pad) {
+  const int b = blockIdx.y;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= ld_pad) return;
+  float v = 0.f;
+  if (j < L + 2 * pad) {
+    int s = j - pad;
+    if (s < 0) s = -s;                       // reflect (edge sample not repeated)
+    if (s >= L) s = 2 * (L - 1) - s;
+    v = __ldg(wave + (size_t)b * L + s);
+  }
+  const size_t o = (size_t)b * ld_pad + j;
+  if (kSplit) {
+    bf16 h = __float2bfloat16_rn(v);
+    bf16 l = __float2bfloat16_rn(v - __bfloat162float(h));
+    reinterpret_cast<bf16*>(hi_)[o] = h;
+    reinterpret_cast<bf16*>(lo_)[o] = l;
+  } else {
+    reinterpret_cast<float*>(hi_)[o] = v;
+  }
+}
+
+// =============================================================================================
+// power -> mel -> log -> bn0 (fp32-accurate path; spectrogram materialised by the SIMT GEMM)
+// =============================================================================================
+__global__ void power_mel_log_kernel(const float* __restrict__ spec, int ld_spec, int n_bins,
+                                     const float* __restrict__ melT, const int32_t* __restrict__ mel_lo,
+                                     const int32_t* __restrict__ mel_hi, const float* __restrict__ bn_scale,
+                                     const float* __restrict__ bn_shift, float* __restrict__ out, int rows,
+                                     int n_mels) {
+  extern __shared__ float p[];
+  const int r = blockIdx.x;
+  const float* s = spec + (size_t)r * ld_spec;
+  for (int k = threadIdx.x; k < n_bins; k += blockDim.x) {
+    const float re = s[k], im = s[n_bins + k];
+    p[k] = re * re + im * im;
+  }
+  __syncthreads();
+  for (int m = threadIdx.x; m < n_mels; m += blockDim.x) {
+    const int lo = mel_lo[m], hi = mel_hi[m];
+    const float* w = melT + (size_t)m * n_bins;
+    float acc = 0.f;
+    for (int k = lo; k < hi; ++k) acc = fmaf(p[k], w[k], acc);
+    const float db = 10.0f * log10f(fmaxf(acc, 1e-10f));
+    out[(size_t)r * n_mels + m] = db * bn_scale[m] + bn_shift[m];
+  }
+}
+
+// =============================================================================================
+// stem: 4x4 stride-4 conv over (T, 224) with 4 rows of zero padding in time, then LayerNorm(96)
+// one warp per output pixel; lane l owns channels l, l+32, l+64.
+// =============================================================================================
+template <typename T>
+__global__ void __launch_bounds__(256) stem_kernel(const float* __restrict__ logmel, const float* __restrict__ w,
+                                                   const float* __restrict__ bias, const float* __restrict__ ln_w,
+                                                   const float* __restrict__ ln_b, T* __restrict__ out, int B,
+                                                   int Tn, int n_mels, int H0, int W0, int pix_per_warp) {
+  constexpr int CO = 96;
+  __shared__ float sw[16 * CO];
+  for (int i = threadIdx.x; i < 16 * CO; i += blockDim.x) sw[i] = w[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const long long total = (long long)B * H0 * W0;
+  long long pix0 = ((long long)blockIdx.x * (blockDim.x >> 5) + warp) * pix_per_warp;
+  float bv[3], gw[3], gb[3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    bv[j] = bias[lane + 32 * j];
+    gw[j] = ln_w[lane + 32 * j];
+    gb[j] = ln_b[lane + 32 * j];
+  }
+  for (int i = 0; i < pix_per_warp; ++i) {
+    const long long pix = pix0 + i;
+    if (pix >= total) break;
+    const int ox = (int)(pix % W0);
+    const int oy = (int)((pix / W0) % H0);
+    const int b = (int)(pix / ((long long)W0 * H0));
+    // lanes 0..15 fetch the 16 patch values (ky = lane/4, kx = lane%4)
+    float v = 0.f;
+    if (lane < 16) {
+      const int t = oy * 4 - 4 + (lane >> 2);
+      const int m = ox * 4 + (lane & 3);
+      if (t >= 0 && t < Tn) v = __ldg(logmel + ((size_t)b * Tn + t) * n_mels + m);
+    }
+    float acc[3] = {bv[0], bv[1], bv[2]};
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const float xv = __shfl_sync(0xffffffffu, v, k);
+#pragma unroll
+      for (int j = 0; j < 3; ++j) acc[j] = fmaf(xv, sw[k * CO + lane + 32 * j], acc[j]);
+    }
+    const float mean = warp_sum(acc[0] + acc[1] + acc[2]) * (1.0f / CO);
+    float d[3], sq = 0.f;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      d[j] = acc[j] - mean;
+      sq += d[j] * d[j];
+    }
+    const float rstd = rsqrtf(warp_sum(sq) * (1.0f / CO) + 1e-6f);
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+      out[(size_t)pix * CO + lane + 32 * j] = from_float<T>(d[j] * rstd * gw[j] + gb[j]);
+  }
+}
+
+// =============================================================================================
+// depthwise 7x7 + LayerNorm.  Thread = (strip of 7 output pixels along W) x (channel pair).
+// The 49 taps of the thread's two channels live in registers for the whole block lifetime; per
+// input row the thread loads 13 channel-pairs and issues 98 FMAs (7.5 FMA per load).
+// LayerNorm: two-pass; per-pixel partial sums are reduce-scattered inside each 16-lane group
+// (8 shuffles for 7 pixels) and combined across groups with shared-memory atomics.
+// =============================================================================================
+template <int S>
+__device__ __forceinline__ void strip_reduce_add(float (&v)[8], float* red /*[8] of this strip*/, int lane) {
+  // reduce-scatter over lanes differing in bits 3,2,1 of the 16-lane group, then bit 0.
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const bool up = lane & 8;
+    const float send = up ? v[i] : v[i + 4];
+    const float keep = up ? v[i + 4] : v[i];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const bool up = lane & 4;
+    const float send = up ? v[i] : v[i + 2];
+    const float keep = up ? v[i + 2] : v[i];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  {
+    const bool up = lane & 2;
+    const float send = up ? v[0] : v[1];
+    const float keep = up ? v[1] : v[0];
+    v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  }
+  v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+  if ((lane & 1) == 0) {
+    const int p = ((lane & 8) ? 4 : 0) + ((lane & 4) ? 2 : 0) + ((lane & 2) ? 1 : 0);
+    if (p < 7) atomicAdd(red + p, v[0]);
+  }
+}
+
+template <typename T, int C, int S, int ROWS>
+__global__ void __launch_bounds__(S* C / 2)
+    dwconv_ln_kernel(const T* __restrict__ x, const T* __restrict__ w, const float* __restrict__ bias,
+                     const float* __restrict__ ln_w, const float* __restrict__ ln_b, T* __restrict__ y, int H,
+                     int W) {
+  using P = Pair<T>;
+  using PT = typename P::type;
+  constexpr int TPS = C / 2;  // threads per strip
+  __shared__ float red[2][2][S][8];  // [buffer][sum | sumsq][strip][pixel]
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const int cp = tid % TPS;
+  const int s = tid / TPS;
+  const int strip = blockIdx.x * S + s;
+  const int w0 = strip * 7;
+  const int b = blockIdx.z;
+  const int h_begin = blockIdx.y * ROWS;
+  const PT* xp = reinterpret_cast<const PT*>(x) + (size_t)b * H * W * TPS;
+  PT* yp = reinterpret_cast<PT*>(y) + (size_t)b * H * W * TPS;
+
+  for (int i = tid; i < 2 * 2 * S * 8; i += S * TPS) (&red[0][0][0][0])[i] = 0.f;
+
+  PT wr[49];
+#pragma unroll
+  for (int k = 0; k < 49; ++k) wr[k] = reinterpret_cast<const PT*>(w)[k * TPS + cp];
+  const float2 bs = make_float2(bias[2 * cp], bias[2 * cp + 1]);
+  const float2 gw = make_float2(ln_w[2 * cp], ln_w[2 * cp + 1]);
+  const float2 gb = make_float2(ln_b[2 * cp], ln_b[2 * cp + 1]);
+  __syncthreads();
+
+  for (int r = 0; r < ROWS; ++r) {
+    const int h = h_begin + r;
+    if (h >= H) break;  // block-uniform
+    const int buf = r & 1;
+    float2 acc[7];
+#pragma unroll
+    for (int p = 0; p < 7; ++p) acc[p] = bs;
+#pragma unroll
+    for (int ky = 0; ky < 7; ++ky) {
+      const int ih = h + ky - 3;
+      if (ih < 0 || ih >= H) continue;  // block-uniform
+      const PT* row = xp + (size_t)ih * W * TPS + cp;
+      float2 in[13];
+#pragma unroll
+      for (int j = 0; j < 13; ++j) {
+        const int iw = w0 - 3 + j;
+        in[j] = (iw >= 0 && iw < W) ? P::unpack(__ldg(row + (size_t)iw * TPS)) : make_float2(0.f, 0.f);
+      }
+#pragma unroll
+      for (int kx = 0; kx < 7; ++kx) {
+        const float2 wv = P::unpack(wr[ky * 7 + kx]);
+#pragma unroll
+        for (int p = 0; p < 7; ++p) {
+          acc[p].x = fmaf(in[p + kx].x, wv.x, acc[p].x);
+          acc[p].y = fmaf(in[p + kx].y, wv.y, acc[p].y);
+        }
+      }
+    }
+    // ---- LayerNorm over C (two-pass, fp32) -------------------------------------------------
+    float v[8];
+#pragma unroll
+    for (int p = 0; p < 7; ++p) v[p] = acc[p].x + acc[p].y;
+    v[7] = 0.f;
+    strip_reduce_add<S>(v, &red[buf][0][s][0], lane);
+    __syncthreads();
+    // safe to clear the other buffer now: its readers all passed this barrier
+    for (int i = tid; i < 2 * S * 8; i += S * TPS) (&red[buf ^ 1][0][0][0])[i] = 0.f;
+    float mean[7];
+#pragma unroll
+    for (int p = 0; p < 7; ++p) {
+      mean[p] = red[buf][0][s][p] * (1.0f / C);
+      acc[p].x -= mean[p];
+      acc[p].y -= mean[p];
+      v[p] = acc[p].x * acc[p].x + acc[p].y * acc[p].y;
+    }
+    v[7] = 0.f;
+    strip_reduce_add<S>(v, &red[buf][1][s][0], lane);
+    __syncthreads();
+    PT* orow = yp + ((size_t)h * W + w0) * TPS + cp;
+#pragma unroll
+    for (int p = 0; p < 7; ++p) {
+      const float rstd = rsqrtf(red[buf][1][s][p] * (1.0f / C) + 1e-6f);
+      orow[(size_t)p * TPS] = P::pack(acc[p].x * rstd * gw.x + gb.x, acc[p].y * rstd * gw.y + gb.y);
+    }
+  }
+}
+
+// =============================================================================================
+// channels_first LayerNorm + 2x2 patch gather: one warp per INPUT pixel.
+// =============================================================================================
+template <typename T>
+__global__ void __launch_bounds__(256)
+    ln_patchify_kernel(const T* __restrict__ x, const float* __restrict__ ln_w, const float* __restrict__ ln_b,
+                       T* __restrict__ a, int B, int H, int W, int C) {
+  using P = Pair<T>;
+  using PT = typename P::type;
+  constexpr int MAXP = 6;  // C <= 384
+  const int lane = threadIdx.x & 31;
+  const int Ho = H / 2, Wo = W / 2;
+  const int half = C / 2;
+  const long long total = (long long)B * Ho * 2 * Wo * 2;
+  const long long pix = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (pix >= total) return;
+  const int wi = (int)(pix % (Wo * 2));
+  const int hi = (int)((pix / (Wo * 2)) % (Ho * 2));
+  const int b = (int)(pix / ((long long)Wo * 2 * Ho * 2));
+  const PT* src = reinterpret_cast<const PT*>(x) + (((size_t)b * H + hi) * W + wi) * half;
+  float2 v[MAXP];
+  float sum = 0.f;
+#pragma unroll
+  for (int j = 0; j < MAXP; ++j) {
+    const int cp = lane + 32 * j;
+    v[j] = (cp < half) ? P::unpack(__ldg(src + cp)) : make_float2(0.f, 0.f);
+    sum += v[j].x + v[j].y;
+  }
+  const float mean = warp_sum(sum) / C;
+  float sq = 0.f;
+#pragma unroll
+  for (int j = 0; j < MAXP; ++j) {
+    const int cp = lane + 32 * j;
+    if (cp < half) {
+      v[j].x -= mean;
+      v[j].y -= mean;
+      sq += v[j].x * v[j].x + v[j].y * v[j].y;
+    }
+  }
+  const float rstd = 1.0f / sqrtf(warp_sum(sq) / C + 1e-6f);
+  const size_t m = ((size_t)b * Ho + (hi >> 1)) * Wo + (wi >> 1);
+  PT* dst = reinterpret_cast<PT*>(a) + m * (size_t)(4 * half) + (size_t)((hi & 1) * 2 + (wi & 1)) * half;
+#pragma unroll
+  for (int j = 0; j < MAXP; ++j) {
+    const int cp = lane + 32 * j;
+    if (cp < half) {
+      const float2 g = *reinterpret_cast<const float2*>(ln_w + 2 * cp);
+      const float2 be = *reinterpret_cast<const float2*>(ln_b + 2 * cp);
+      dst[cp] = P::pack(v[j].x * rstd * g.x + be.x, v[j].y * rstd * g.y + be.y);
+    }
+  }
+}
+
+// =============================================================================================
+// head: one block per clip
+// =============================================================================================
+__device__ __forceinline__ float block_sum_256(float v, float* scratch) {
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) scratch[warp] = v;
+  __syncthreads();
+  float t = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) t += scratch[i];
+  return t;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+    head_kernel(const T* __restrict__ x, const float* __restrict__ ln_w, const float* __restrict__ ln_b,
+                const float* __restrict__ fc_w, const float* __restrict__ fc_b, float* __restrict__ scene,
+                float* __restrict__ logits, float* __restrict__ probs, int H, int W, int C, int n_cls) {
+  constexpr int MAXC = 4;  // C <= 1024
+  extern __shared__ float sv[];  // C floats
+  __shared__ float scratch[8];
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x;
+  const T* xb = x + (size_t)b * H * W * C;
+  float mx[MAXC], sm[MAXC];
+#pragma unroll
+  for (int j = 0; j < MAXC; ++j) {
+    mx[j] = -INFINITY;
+    sm[j] = 0.f;
+  }
+  const float inv_w = 1.0f / W;
+  for (int h = 0; h < H; ++h) {
+#pragma unroll
+    for (int j = 0; j < MAXC; ++j) {
+      const int c = tid + 256 * j;
+      if (c < C) {
+        float s = 0.f;
+        for (int wv = 0; wv < W; ++wv) s += to_float(xb[((size_t)h * W + wv) * C + c]);
+        s *= inv_w;                       // torch.mean(x, dim=3)      CX:279
+        mx[j] = fmaxf(mx[j], s);          // torch.max(x, dim=2)       CX:280
+        sm[j] += s;                       // torch.mean(x, dim=2)      CX:281
+      }
+    }
+  }
+  float val[MAXC], part = 0.f;
+#pragma unroll
+  for (int j = 0; j < MAXC; ++j) {
+    const int c = tid + 256 * j;
+    val[j] = (c < C) ? mx[j] + sm[j] / H : 0.f;   // x1 + x2   CX:282
+    part += val[j];
+  }
+  const float mean = block_sum_256(part, scratch) / C;
+  part = 0.f;
+#pragma unroll
+  for (int j = 0; j < MAXC; ++j) {
+    const int c = tid + 256 * j;
+    if (c < C) {
+      val[j] -= mean;
+      part += val[j] * val[j];
+    }
+  }
+  const float rstd = 1.0f / sqrtf(block_sum_256(part, scratch) / C + 1e-6f);  // nn.LayerNorm(768, eps 1e-6) CX:256
+#pragma unroll
+  for (int j = 0; j < MAXC; ++j) {
+    const int c = tid + 256 * j;
+    if (c < C) {
+      const float o = val[j] * rstd * ln_w[c] + ln_b[c];
+      sv[c] = o;
+      scene[(size_t)b * C + c] = o;
+    }
+  }
+  __syncthreads();
+  if (n_cls <= 0) return;
+  const int lane = tid & 31, warp = tid >> 5;
+  for (int o = warp; o < n_cls; o += 8) {
+    const float* wr = fc_w + (size_t)o * C;
+    float acc = 0.f;
+    for (int k = lane * 4; k < C; k += 128) {
+      const float4 w4 = __ldg(reinterpret_cast<const float4*>(wr + k));
+      acc = fmaf(w4.x, sv[k], acc);
+      acc = fmaf(w4.y, sv[k + 1], acc);
+      acc = fmaf(w4.z, sv[k + 2], acc);
+      acc = fmaf(w4.w, sv[k + 3], acc);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      const float lg = acc + fc_b[o];
+      logits[(size_t)b * n_cls + o] = lg;
+      probs[(size_t)b * n_cls + o] = 1.0f / (1.0f + expf(-lg));
+    }
+  }
+}
+
+// =============================================================================================
+// NHWC (act dtype) -> NCHW fp32
+// =============================================================================================
+template <typename T>
+__global__ void nhwc_to_nchw_kernel(const T* __restrict__ x, float* __restrict__ out, int HW, int C) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const T* xb = x + (size_t)b * HW * C;
+  float* ob = out + (size_t)b * HW * C;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int p = p0 + i, c = c0 + threadIdx.x;
+    if (p < HW && c < C) tile[i][threadIdx.x] = to_float(xb[(size_t)p * C + c]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, p = p0 + threadIdx.x;
+    if (p < HW && c < C) ob[(size_t)c * HW + p] = tile[threadIdx.x][i];
+  }
+}
+
+// ---- launch helpers ---------------------------------------------------------------------------
+template <typename T, int C, int S, int ROWS>
+static int launch_dwconv(const void* x, const void* w, const float* bias, const float* ln_w, const float* ln_b,
+                         void* y, int B, int H, int W, cudaStream_t st) {
+  const int strips = W / 7;
+  ACX_CHECK(strips % S == 0, ACX_ERR_ARG, "dwconv_ln: W/7=%d not a multiple of strips-per-block %d", strips, S);
+  dim3 grid(strips / S, ceil_div(H, ROWS), B);
+  dwconv_ln_kernel<T, C, S, ROWS><<<grid, S * C / 2, 0, st>>>(
+      reinterpret_cast<const T*>(x), reinterpret_cast<const T*>(w), bias, ln_w, ln_b, reinterpret_cast<T*>(y), H, W);
+  ACX_CUDA(cudaGetLastError());
+  return ACX_OK;
+}
+
+template <typename T>
+static int dispatch_dwconv(const void* x, const void* w, const float* bias, const float* ln_w, const float* ln_b,
+                           void* y, int B, int H, int W, int C, cudaStream_t st) {
+  const int strips = W / 7;
+  switch (C) {
+    case 96:
+      if (strips % 4 == 0) return launch_dwconv<T, 96, 4, 4>(x, w, bias, ln_w, ln_b, y, B, H, W, st);
+      if (strips % 2 == 0) return launch_dwconv<T, 96, 2, 4>(x, w, bias, ln_w, ln_b, y, B, H, W, st);
+      return launch_dwconv<T, 96, 1, 4>(x, w, bias, ln_w, ln_b, y, B, H, W, st);
+    case 192:
+      if (strips % 2 == 0) return launch_dwconv<T, 192, 2, 4>(x, w, bias, ln_w, ln_b, y, B, H, W, st);
+      return launch_dwconv<T, 192, 1, 4>(x, w, bias, ln_w, ln_b, y, B, H, W, st);
+    case 384:
+      return launch_dwconv<T, 384, 1, 4>(x, w, bias, ln_w, ln_b, y, B, H, W, st);
+    case 768:
+      return launch_dwconv<T, 768, 1, 4>(x, w, bias, ln_w, ln_b, y, B, H, W, st);
+    default:
+      set_error("dwconv_ln: unsupported channel count %d (ConvNeXt-Tiny dims are 96/192/384/768)", C);
+      return ACX_ERR_UNSUPPORTED;
+  }
+}
+
+}  // namespace acx
+
+using namespace acx;
+
+extern "C" {
+
+int acx_wave_prep(const float* wave, void* hi, void* lo, int B, int L, int n_fft, int ld_pad, int act_dtype,
+                  void* stream) {
+  ACX_CHECK(wave && hi && B > 0 && L > 0, ACX_ERR_ARG, "wave_prep: null pointer or empty batch");
+  ACX_CHECK(L > n_fft / 2, ACX_ERR_ARG, "wave_prep: reflect padding needs L > n_fft/2 (L=%d)", L);
+  ACX_CHECK(ld_pad >= L + n_fft && ld_pad % 8 == 0, ACX_ERR_ARG, "wave_prep: ld_pad=%d must be >= L+n_fft and %%8==0",
+            ld_pad);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  dim3 grid(ceil_div(ld_pad, 256), B);
+  if (act_dtype == ACX_BF16) {
+    ACX_CHECK(lo != nullptr, ACX_ERR_ARG, "wave_prep: lo buffer required for bf16 split");
+    wave_prep_kernel<true><<<grid, 256, 0, st>>>(wave, hi, lo, L, n_fft / 2, ld_pad);
+  } else {
+    wave_prep_kernel<false><<<grid, 256, 0, st>>>(wave, hi, lo, L, n_fft / 2, ld_pad);
+  }
+  ACX_CUDA(cudaGetLastError());
+  return ACX_OK;
+}
+
+int acx_power_mel_log(const float* spec, int ld_spec, int n_bins, const float* melT, const int32_t* mel_lo,
+                      const int32_t* mel_hi, const float* bn_scale, const float* bn_shift, float* out, int rows,
+                      int n_mels, void* stream) {
+  ACX_CHECK(spec && melT && mel_lo && mel_hi && bn_scale && bn_shift && out, ACX_ERR_ARG, "power_mel_log: null pointer");
+  ACX_CHECK(rows > 0 && n_bins > 0 && n_bins <= 8192, ACX_ERR_ARG, "power_mel_log: bad sizes");
+  power_mel_log_kernel<<<rows, 256, n_bins * sizeof(float), reinterpret_cast<cudaStream_t>(stream)>>>(
+      spec, ld_spec, n_bins, melT, mel_lo, mel_hi, bn_scale, bn_shift, out, rows, n_mels);
+  ACX_CUDA(cudaGetLastError());
+  return ACX_OK;
+}
+
+int acx_stem(const float* logmel, const float* w, const float* bias, const float* ln_w, const float* ln_b, void* out,
+             int B, int T, int n_mels, int act_dtype, void* stream) {
+  ACX_CHECK(logmel && w && bias && ln_w && ln_b && out, ACX_ERR_ARG, "stem: null pointer");
+  ACX_CHECK(n_mels % 4 == 0 && B > 0 && T > 0, ACX_ERR_ARG, "stem: n_mels must be a multiple of 4");
+  const int H0 = (T + 4) / 4 + 1, W0 = n_mels / 4;
+  const long long total = (long long)B * H0 * W0;
+  const int ppw = 8;
+  const int blocks = (int)((total + 8 * ppw - 1) / (8 * ppw));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (act_dtype == ACX_BF16)
+    stem_kernel<bf16><<<blocks, 256, 0, st>>>(logmel, w, bias, ln_w, ln_b, reinterpret_cast<bf16*>(out), B, T, n_mels,
+                                              H0, W0, ppw);
+  else
+    stem_kernel<float><<<blocks, 256, 0, st>>>(logmel, w, bias, ln_w, ln_b, reinterpret_cast<float*>(out), B, T,
+                                               n_mels, H0, W0, ppw);
+  ACX_CUDA(cudaGetLastError());
+  return ACX_OK;
+}
+
+int acx_dwconv_ln(const void* x, const void* w, const float* bias, const float* ln_w, const float* ln_b, void* y, int B,
+                  int H, int W, int C, int act_dtype, void* stream) {
+  ACX_CHECK(x && w && bias && ln_w && ln_b && y, ACX_ERR_ARG, "dwconv_ln: null pointer");
+  ACX_CHECK(B > 0 && H > 0 && W > 0 && W % 7 == 0, ACX_ERR_ARG, "dwconv_ln: W=%d must be a positive multiple of 7", W);
+  ACX_CHECK(B <= 65535, ACX_ERR_ARG, "dwconv_ln: batch %d exceeds gridDim.z", B);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  return act_dtype == ACX_BF16 ? dispatch_dwconv<bf16>(x, w, bias, ln_w, ln_b, y, B, H, W, C, st)
+                               : dispatch_dwconv<float>(x, w, bias, ln_w, ln_b, y, B, H, W, C, st);
+}
+
+int acx_ln_patchify(const void* x, const float* ln_w, const float* ln_b, void* a, int B, int H, int W, int C,
+                    int act_dtype, void* stream) {
+  ACX_CHECK(x && ln_w && ln_b && a, ACX_ERR_ARG, "ln_patchify: null pointer");
+  ACX_CHECK(C % 2 == 0 && C <= 384 && H >= 2 && W >= 2, ACX_ERR_ARG, "ln_patchify: unsupported shape C=%d H=%d W=%d", C,
+            H, W);
+  const long long total = (long long)B * (H / 2) * 2 * (W / 2) * 2;
+  const int blocks = (int)((total + 7) / 8);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (act_dtype == ACX_BF16)
+    ln_patchify_kernel<bf16><<<blocks, 256, 0, st>>>(reinterpret_cast<const bf16*>(x), ln_w, ln_b,
+                                                     reinterpret_cast<bf16*>(a), B, H, W, C);
+  else
+    ln_patchify_kernel<float><<<blocks, 256, 0, st>>>(reinterpret_cast<const float*>(x), ln_w, ln_b,
+                                                      reinterpret_cast<float*>(a), B, H, W, C);
+  ACX_CUDA(cudaGetLastError());
+  return ACX_OK;
+}
+
+int acx_head(const void* x, const float* ln_w, const float* ln_b, const float* fc_w, const float* fc_b, float* scene,
+             float* logits, float* probs, int B, int H, int W, int C, int n_cls, int act_dtype, void* stream) {
+  ACX_CHECK(x && ln_w && ln_b && scene, ACX_ERR_ARG, "head: null pointer");
+  ACX_CHECK(n_cls == 0 || (fc_w && fc_b && logits && probs), ACX_ERR_ARG, "head: fc pointers required when n_cls>0");
+  ACX_CHECK(C % 4 == 0 && C <= 1024 && B > 0 && H > 0 && W > 0, ACX_ERR_ARG, "head: unsupported shape");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (act_dtype == ACX_BF16)
+    head_kernel<bf16><<<B, 256, C * sizeof(float), st>>>(reinterpret_cast<const bf16*>(x), ln_w, ln_b, fc_w, fc_b,
+                                                         scene, logits, probs, H, W, C, n_cls);
+  else
+    head_kernel<float><<<B, 256, C * sizeof(float), st>>>(reinterpret_cast<const float*>(x), ln_w, ln_b, fc_w, fc_b,
+                                                          scene, logits, probs, H, W, C, n_cls);
+  ACX_CUDA(cudaGetLastError());
+  return ACX_OK;
+}
+
+int acx_nhwc_to_nchw_f32(const void* x, float* out, int B, int H, int W, int C, int act_dtype, void* stream) {
+  ACX_CHECK(x && out && B > 0 && B <= 65535, ACX_ERR_ARG, "nhwc_to_nchw: bad arguments");
+  const int HW = H * W;
+  dim3 grid(ceil_div(HW, 32), ceil_div(C, 32), B), block(32, 8);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (act_dtype == ACX_BF16)
+    nhwc_to_nchw_kernel<bf16><<<grid, block, 0, st>>>(reinterpret_cast<const bf16*>(x), out, HW, C);
+  else
+    nhwc_to_nchw_kernel<float><<<grid, block, 0, st>>>(reinterpret_cast<const float*>(x), out, HW, C);
+  ACX_CUDA(cudaGetLastError());
+  return ACX_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,53 @@
+// Host-side TMA tensor-map construction (cuTensorMapEncodeTiled resolved through the runtime so the
+// library links against cudart only and still loads on a box without libcuda).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include "common.cuh"
+
+namespace acx {
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static inline PFN_encodeTiled get_encode_tiled() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  return fn;
+}
+
+// Generic rank-R bf16 map, 128B swizzle, OOB reads return zero.
+// dims[0] is the contiguous dimension; strides_bytes[i] is the byte stride of dims[i+1].
+static inline int make_tmap_bf16(CUtensorMap* tm, const void* base, int rank, const cuuint64_t* dims,
+                                 const cuuint64_t* strides_bytes, const cuuint32_t* box) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  ACX_CHECK(enc != nullptr, ACX_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims,
+                   strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  ACX_CHECK(r == CUDA_SUCCESS, ACX_ERR_CUDA,
+            "cuTensorMapEncodeTiled failed (CUresult %d; rank %d dims %llu x %llu, stride %llu B, box %u x %u)", (int)r,
+            rank, (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)strides_bytes[0],
+            box[0], box[1]);
+  return ACX_OK;
+}
+
+// Row-major (rows, cols) bf16 matrix, box = box_cols x box_rows.
+static inline int make_tmap_2d_bf16(CUtensorMap* tm, const void* base, uint64_t cols, uint64_t rows,
+                                    uint64_t row_stride_bytes, uint32_t box_cols, uint32_t box_rows) {
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {row_stride_bytes};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  return make_tmap_bf16(tm, base, 2, dims, strides, box);
+}
+
+}  // namespace acx

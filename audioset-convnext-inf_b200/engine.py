@@ -1,0 +1,272 @@
+"""Host-side orchestration of the hot path: weight repacking, workspace, kernel sequence.
+
+Everything that touches numbers runs in libacx.so (hand-written sm_100a CUDA behind the C ABI in
+include/acx.h); PyTorch only owns device memory and the stream.  Two arithmetic modes:
+
+  "bf16"  activations / GEMM operands bf16, fp32 accumulation in TMEM (tcgen05), fp32 LayerNorm
+          statistics; the front end runs split-bf16 (x3) so the log-mel keeps fp32-level accuracy.
+  "fp32"  the fp32-accurate mode: same bandwidth kernels instantiated for float, SIMT fp32 GEMMs.
+
+Kernel order per chunk of clips (reference convnext.py:287-331, forward_features :269-285):
+  wave_prep -> front end -> stem -> [dwconv_ln -> pwconv1+GELU -> pwconv2+gamma+residual] x (3,3,9,3)
+  with ln_patchify + GEMM between stages -> head (pool + LayerNorm + fc + sigmoid) / frame transpose.
+"""
+import os
+
+import torch
+
+from . import _native as N
+
+DEPTHS = (3, 3, 9, 3)
+DIMS = (96, 192, 384, 768)
+N_FFT, HOP, N_MELS, N_BINS, N_CLASSES = 1024, 320, 224, 513, 527
+BN0_EPS = 1e-5
+
+
+def _p(t):
+    return 0 if t is None else t.data_ptr()
+
+
+class PackedWeights:
+    """Kernel-friendly copies of the 190-entry state dict.  Built once per
+    (device, precision); the module drops it whenever parameters may have changed."""
+
+    def __init__(self, sd, device, precision):
+        assert precision in ("bf16", "fp32")
+        self.precision = precision
+        self.device = device
+        adt = torch.bfloat16 if precision == "bf16" else torch.float32
+        self.act_dtype = adt
+        f32 = dict(device=device, dtype=torch.float32)
+
+        def g(key):
+            return sd[key].detach().to(**f32)
+
+        # ---- front end -----------------------------------------------------------------------
+        conv_real = g("spectrogram_extractor.stft.conv_real.weight")[:, 0, :]   # (513, 1024)
+        conv_imag = g("spectrogram_extractor.stft.conv_imag.weight")[:, 0, :]
+        melW = g("logmel_extractor.melW")                                         # (513, 224)
+        assert conv_real.shape == (N_BINS, N_FFT) and melW.shape == (N_BINS, N_MELS), \
+            "only the n_fft=1024 / 224-mel front end of convnext_tiny is supported"
+        scale = g("bn0.weight") / torch.sqrt(g("bn0.running_var") + BN0_EPS)
+        self.bn_scale = scale.contiguous()
+        self.bn_shift = (g("bn0.bias") - g("bn0.running_mean") * scale).contiguous()
+        # fp32-accurate path: dense windowed-DFT rows (re | im) and banded mel
+        self.dft_f32 = torch.cat([conv_real, conv_imag], 0).contiguous()         # (1026, 1024)
+        self.melT = melW.t().contiguous()                                          # (224, 513)
+        nz = melW != 0
+        idx = torch.arange(N_BINS, device=device)[:, None].expand(N_BINS, N_MELS)
+        big = torch.full_like(idx, N_BINS)
+        lo = torch.where(nz, idx, big).min(0).values
+        hi = torch.where(nz, idx + 1, torch.zeros_like(idx)).max(0).values
+        lo = torch.minimum(lo, hi)
+        self.mel_lo = lo.to(torch.int32).contiguous()
+        self.mel_hi = hi.to(torch.int32).contiguous()
+        # tensor-core path: 64-bin chunks; only bins that feed a non-zero mel weight are computed
+        used = nz.any(1).nonzero().flatten()
+        k_end = int(used.max().item()) + 1 if used.numel() else 1
+        self.n_chunks = (k_end + 63) // 64
+        if precision == "bf16":
+            nb = self.n_chunks * 64
+            re = torch.zeros(nb, N_FFT, **f32)
+            im = torch.zeros(nb, N_FFT, **f32)
+            m = min(nb, N_BINS)
+            re[:m], im[:m] = conv_real[:m], conv_imag[:m]
+            dft = torch.stack([re.view(self.n_chunks, 64, N_FFT), im.view(self.n_chunks, 64, N_FFT)], 1)
+            dft = dft.reshape(self.n_chunks * 128, N_FFT)
+            self.dft_hi, self.dft_lo = _split_bf16(dft)
+            mw = torch.zeros(nb, 256, **f32)
+            mw[:m, :N_MELS] = melW[:m]
+            mel = mw.view(self.n_chunks, 64, 256).transpose(1, 2).reshape(self.n_chunks * 256, 64)
+            self.melc_hi, self.melc_lo = _split_bf16(mel)
+
+        # ---- stem ---------------------------------------------------------------------------
+        self.stem_w = g("downsample_layers.0.0.weight").reshape(DIMS[0], 16).t().contiguous()  # (16, 96)
+        self.stem_b = g("downsample_layers.0.0.bias").contiguous()
+        self.stem_ln_w = g("downsample_layers.0.1.weight").contiguous()
+        self.stem_ln_b = g("downsample_layers.0.1.bias").contiguous()
+
+        # ---- downsample layers 1..3 ---------------------------------------------------------
+        self.ds = []
+        for i in range(1, 4):
+            w = g(f"downsample_layers.{i}.1.weight")                 # (Cout, Cin, 2, 2)
+            cout, cin = w.shape[0], w.shape[1]
+            self.ds.append(dict(
+                ln_w=g(f"downsample_layers.{i}.0.weight").contiguous(),
+                ln_b=g(f"downsample_layers.{i}.0.bias").contiguous(),
+                w=w.permute(0, 2, 3, 1).reshape(cout, 4 * cin).to(adt).contiguous(),   # k = (dy, dx, cin)
+                b=g(f"downsample_layers.{i}.1.bias").contiguous()))
+
+        # ---- blocks -------------------------------------------------------------------------
+        self.blocks = []
+        for s in range(4):
+            C = DIMS[s]
+            stage = []
+            for j in range(DEPTHS[s]):
+                p = f"stages.{s}.{j}."
+                stage.append(dict(
+                    dw_w=g(p + "dwconv.weight").reshape(C, 49).t().to(adt).contiguous(),   # (49, C)
+                    dw_b=g(p + "dwconv.bias").contiguous(),
+                    ln_w=g(p + "norm.weight").contiguous(), ln_b=g(p + "norm.bias").contiguous(),
+                    w1=g(p + "pwconv1.weight").to(adt).contiguous(), b1=g(p + "pwconv1.bias").contiguous(),
+                    w2=g(p + "pwconv2.weight").to(adt).contiguous(), b2=g(p + "pwconv2.bias").contiguous(),
+                    gamma=g(p + "gamma").contiguous()))
+            self.blocks.append(stage)
+
+        # ---- head ---------------------------------------------------------------------------
+        self.norm_w, self.norm_b = g("norm.weight").contiguous(), g("norm.bias").contiguous()
+        self.fc_w, self.fc_b = g("head_audioset.weight").contiguous(), g("head_audioset.bias").contiguous()
+
+
+def _split_bf16(x):
+    hi = x.to(torch.bfloat16)
+    lo = (x - hi.to(torch.float32)).to(torch.bfloat16)
+    return hi.contiguous(), lo.contiguous()
+
+
+def out_time_dims(L):
+    """Frame count and per-stage heights for an L-sample clip."""
+    T = L // HOP + 1
+    H0 = (T + 4) // 4 + 1          # Conv2d(k=4, s=4, pad=(4,0)) over time
+    hs = [H0, H0 // 2, (H0 // 2) // 2, ((H0 // 2) // 2) // 2]
+    return T, hs
+
+
+class Engine:
+    def __init__(self, state_dict, device, precision="bf16", chunk=None, frontend=None, mlp=None):
+        self.lib = N.load()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise N.NativeError("the B200 engine needs a CUDA device; there is no CPU path")
+        with torch.cuda.device(self.device):
+            if not self.lib.acx_device_ok():
+                raise N.NativeError(N.last_error())
+        self.precision = precision
+        self.w = PackedWeights(state_dict, self.device, precision)
+        self.adt = N.ACX_BF16 if precision == "bf16" else N.ACX_F32
+        self.esize = 2 if precision == "bf16" else 4
+        self.chunk = int(chunk or os.environ.get("ACX_CHUNK", 32 if precision == "bf16" else 4))
+        # which implementation of the two fusable pieces to run (both are libacx kernels)
+        self.frontend = frontend or os.environ.get("ACX_FRONTEND", "fused" if precision == "bf16" else "simt")
+        self.mlp = mlp or os.environ.get("ACX_MLP", "gemm")
+        if precision == "fp32":
+            self.frontend, self.mlp = "simt", "gemm"
+        self._ws = {}
+
+    # ---- workspace ------------------------------------------------------------------------------
+    def _workspace(self, n, L):
+        key = (n, L)
+        ws = self._ws.get(key)
+        if ws is not None:
+            return ws
+        T, hs = out_time_dims(L)
+        dev = self.device
+        adt = self.w.act_dtype
+        ld_pad = (L + N_FFT + 7) // 8 * 8
+        ws = dict(T=T, hs=hs, ld_pad=ld_pad)
+        if self.frontend == "fused":
+            ws["wav_hi"] = torch.empty(n, ld_pad, device=dev, dtype=torch.bfloat16)
+            ws["wav_lo"] = torch.empty(n, ld_pad, device=dev, dtype=torch.bfloat16)
+        else:
+            ws["wav_pad"] = torch.empty(n, ld_pad, device=dev, dtype=torch.float32)
+            ws["spec"] = torch.empty(n * T, 2 * N_BINS, device=dev, dtype=torch.float32)
+        ws["logmel"] = torch.empty(n, T, N_MELS, device=dev, dtype=torch.float32)
+        m0 = n * hs[0] * 56
+        ws["x"] = torch.empty(m0 * DIMS[0], device=dev, dtype=adt)
+        ws["y"] = torch.empty(m0 * DIMS[0], device=dev, dtype=adt)
+        ws["hid"] = torch.empty(m0 * 4 * DIMS[0], device=dev, dtype=adt)
+        self._ws.clear()          # keep one shape resident
+        self._ws[key] = ws
+        return ws
+
+    # ---- stages (each is one libacx call) ----------------------------------------------------------
+    def _frontend(self, wave, ws, n, L, st):
+        w = self.w
+        T, ld_pad = ws["T"], ws["ld_pad"]
+        if self.frontend == "fused":
+            N.call("acx_wave_prep", wave.data_ptr(), ws["wav_hi"].data_ptr(), ws["wav_lo"].data_ptr(), n, L, N_FFT,
+                   ld_pad, N.ACX_BF16, st)
+            N.call("acx_frontend_fused", ws["wav_hi"].data_ptr(), ws["wav_lo"].data_ptr(), ld_pad,
+                   w.dft_hi.data_ptr(), w.dft_lo.data_ptr(), w.melc_hi.data_ptr(), w.melc_lo.data_ptr(), w.n_chunks,
+                   w.bn_scale.data_ptr(), w.bn_shift.data_ptr(), ws["logmel"].data_ptr(), n, T, N_FFT, HOP, N_MELS, st)
+        else:
+            N.call("acx_wave_prep", wave.data_ptr(), ws["wav_pad"].data_ptr(), 0, n, L, N_FFT, ld_pad, N.ACX_F32, st)
+            N.call("acx_gemm_f32", ws["wav_pad"].data_ptr(), ld_pad, T, HOP, w.dft_f32.data_ptr(),
+                   ws["spec"].data_ptr(), 2 * N_BINS, n * T, 2 * N_BINS, N_FFT, N.EPI_BIAS, 0, 0, 0, st)
+            N.call("acx_power_mel_log", ws["spec"].data_ptr(), 2 * N_BINS, N_BINS, w.melT.data_ptr(),
+                   w.mel_lo.data_ptr(), w.mel_hi.data_ptr(), w.bn_scale.data_ptr(), w.bn_shift.data_ptr(),
+                   ws["logmel"].data_ptr(), n * T, N_MELS, st)
+
+    def _gemm(self, a, wt, out, M, Nn, K, epi, bias, gamma, resid, st):
+        if self.precision == "bf16":
+            N.call("acx_gemm_bf16", a, wt, out, M, Nn, K, epi, bias, gamma, resid, st)
+        else:
+            N.call("acx_gemm_f32", a, M * K, M, K, wt, out, Nn, M, Nn, K, epi, bias, gamma, resid, st)
+
+    def _trunk(self, ws, n, st):
+        w = self.w
+        x, y, hid = ws["x"].data_ptr(), ws["y"].data_ptr(), ws["hid"].data_ptr()
+        N.call("acx_stem", ws["logmel"].data_ptr(), w.stem_w.data_ptr(), w.stem_b.data_ptr(),
+               w.stem_ln_w.data_ptr(), w.stem_ln_b.data_ptr(), x, n, ws["T"], N_MELS, self.adt, st)
+        Wd = 56
+        for s in range(4):
+            C, H = DIMS[s], ws["hs"][s]
+            M = n * H * Wd
+            for blk in w.blocks[s]:
+                N.call("acx_dwconv_ln", x, blk["dw_w"].data_ptr(), blk["dw_b"].data_ptr(), blk["ln_w"].data_ptr(),
+                       blk["ln_b"].data_ptr(), y, n, H, Wd, C, self.adt, st)
+                if self.mlp == "fused" and C in (96, 192):
+                    N.call("acx_mlp_fused", y, x, blk["w1"].data_ptr(), blk["b1"].data_ptr(), blk["w2"].data_ptr(),
+                           blk["b2"].data_ptr(), blk["gamma"].data_ptr(), M, C, st)
+                else:
+                    self._gemm(y, blk["w1"].data_ptr(), hid, M, 4 * C, C, N.EPI_BIAS_GELU, blk["b1"].data_ptr(), 0, 0, st)
+                    self._gemm(hid, blk["w2"].data_ptr(), x, M, C, 4 * C, N.EPI_BIAS_SCALE_RESID,
+                               blk["b2"].data_ptr(), blk["gamma"].data_ptr(), x, st)
+            if s < 3:
+                d = w.ds[s]
+                N.call("acx_ln_patchify", x, d["ln_w"].data_ptr(), d["ln_b"].data_ptr(), y, n, H, Wd, C, self.adt, st)
+                Wd //= 2
+                Mo = n * ws["hs"][s + 1] * Wd
+                self._gemm(y, d["w"].data_ptr(), x, Mo, 2 * C, 4 * C, N.EPI_BIAS, d["b"].data_ptr(), 0, 0, st)
+
+    # ---- public -----------------------------------------------------------------------------------
+    def run(self, wave, want=("logits",)):
+        """wave: (B, L) float32 CUDA tensor.  want: subset of {"logits", "scene", "frame", "logmel"}.
+        Returns dict of fp32 tensors: probs/logits (B,527), scene (B,768), frame (B,768,T',7)."""
+        assert wave.is_cuda and wave.dim() == 2 and wave.dtype == torch.float32 and wave.is_contiguous()
+        B, L = wave.shape
+        T, hs = out_time_dims(L)
+        if hs[3] < 1:
+            raise ValueError(f"clip of {L} samples is too short for the 4-stage trunk")
+        dev = self.device
+        out = {}
+        need_head = "logits" in want or "scene" in want
+        f32 = dict(device=dev, dtype=torch.float32)
+        with torch.cuda.device(dev):
+            st = torch.cuda.current_stream(dev).cuda_stream
+            if need_head:
+                out["scene"] = torch.empty(B, DIMS[3], **f32)
+                out["logits"] = torch.empty(B, N_CLASSES, **f32)
+                out["probs"] = torch.empty(B, N_CLASSES, **f32)
+            if "frame" in want:
+                out["frame"] = torch.empty(B, DIMS[3], hs[3], 7, **f32)
+            if "logmel" in want:
+                out["logmel"] = torch.empty(B, T, N_MELS, **f32)
+            for b0 in range(0, B, self.chunk):
+                n = min(self.chunk, B - b0)
+                ws = self._workspace(min(self.chunk, B), L)
+                self._frontend(wave[b0:b0 + n], ws, n, L, st)
+                if "logmel" in want:
+                    out["logmel"][b0:b0 + n].copy_(ws["logmel"][:n])
+                    if len(want) == 1:
+                        continue
+                self._trunk(ws, n, st)
+                x = ws["x"].data_ptr()
+                if need_head:
+                    w = self.w
+                    N.call("acx_head", x, w.norm_w.data_ptr(), w.norm_b.data_ptr(), w.fc_w.data_ptr(),
+                           w.fc_b.data_ptr(), out["scene"][b0:].data_ptr(), out["logits"][b0:].data_ptr(),
+                           out["probs"][b0:].data_ptr(), n, hs[3], 7, DIMS[3], N_CLASSES, self.adt, st)
+                if "frame" in want:
+                    N.call("acx_nhwc_to_nchw_f32", x, out["frame"][b0:].data_ptr(), n, hs[3], 7, DIMS[3], self.adt, st)
+        return out

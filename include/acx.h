@@ -1,0 +1,123 @@
+/*
+ * libacx -- C ABI of the B200-native audioset-convnext inference hot path.
+ *
+ * The reference (topel/audioset-convnext-inf) is pure Python/PyTorch and has NO FFI, plugin
+ * or operator interface: its boundary is the Python class API of
+ *   src/audioset_convnext_inf/pytorch/convnext.py  (ConvNeXt.forward :287-331,
+ *   forward_scene_embeddings :333-366, forward_frame_embeddings :369-402).
+ * This header is therefore the interface a maintainer of the reference would bind with
+ * ctypes underneath those three methods; every entry point cites the
+ * reference lines whose computation it replaces.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; all pointers are DEVICE pointers unless suffixed _host.
+ *  - every call is asynchronous on `stream` (a cudaStream_t passed as void*), never
+ *    synchronises, never allocates persistent device memory; the caller (torch) owns all
+ *    buffers, including the workspace.
+ *  - return 0 on success, non-zero ACX_ERR_* otherwise; acx_last_error() gives the message
+ *    (thread-local).  No C++ exceptions cross this boundary.
+ *  - activations are channels-last (N, H, W, C) with H = time, W = mel;
+ *    `act_dtype` = ACX_BF16 (tensor-core path) or ACX_F32 (fp32-accurate SIMT path).
+ */
+#ifndef ACX_H_
+#define ACX_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ACX_VERSION 100
+#define ACX_API __attribute__((visibility("default")))
+
+enum { ACX_OK = 0, ACX_ERR_ARG = 1, ACX_ERR_CUDA = 2, ACX_ERR_UNSUPPORTED = 3, ACX_ERR_WORKSPACE = 4 };
+enum { ACX_BF16 = 0, ACX_F32 = 1 };
+
+/* GEMM epilogues (acx_gemm). */
+enum {
+  ACX_EPI_BIAS = 0,            /* out = acc + bias[n]                                  (CX:231-234 conv) */
+  ACX_EPI_BIAS_GELU = 1,       /* out = gelu_erf(acc + bias[n])                         (CX:79-80)        */
+  ACX_EPI_BIAS_SCALE_RESID = 2 /* out = resid[m,n] + gamma[n] * (acc + bias[n])         (CX:81-86)        */
+};
+
+ACX_API int acx_version(void);
+ACX_API const char* acx_last_error(void);
+/* 1 if the current device is compute capability 10.x (B200), else 0 (and sets last error). */
+ACX_API int acx_device_ok(void);
+
+/* ---- front end: torchlibrosa Spectrogram + LogmelFilterBank + bn0 (CX:298-306) ------------- */
+
+/* Reflect-pad n_fft/2 both sides (torchlibrosa STFT.forward: F.pad(..., mode='reflect')) and
+ * split each fp32 sample into bf16 hi + lo (x ~= hi + lo).  wave (B, L) fp32 ->
+ * hi, lo (B, ld_pad) bf16 with ld_pad >= L + n_fft, ld_pad % 8 == 0.  If act_dtype == ACX_F32
+ * writes one fp32 padded array to `hi` and ignores `lo`. */
+ACX_API int acx_wave_prep(const float* wave, void* hi, void* lo, int B, int L, int n_fft, int ld_pad,
+                  int act_dtype, void* stream);
+
+/* fp32-accurate path: spec (B*T, 2*n_bins) fp32 (re | im, from acx_gemm_f32 on the padded wave)
+ * -> power -> mel (sparse band form) -> 10*log10(max(.,1e-10)) -> bn0 affine.
+ * mel_lo/mel_hi (n_mels) int32 give each filter's non-zero bin range [lo, hi); melT is
+ * (n_mels, n_bins) fp32 (transposed melW); bn_scale/bn_shift (n_mels) fold bn0 (eps 1e-5). */
+ACX_API int acx_power_mel_log(const float* spec, int ld_spec, int n_bins, const float* melT, const int32_t* mel_lo,
+                      const int32_t* mel_hi, const float* bn_scale, const float* bn_shift, float* out,
+                      int rows, int n_mels, void* stream);
+
+/* tensor-core path: one fused kernel, frames x DFT (split-bf16 x3, fp32 accumulate in TMEM) ->
+ * power -> x mel (split-bf16 x3) -> log10 -> bn0; never writes the spectrogram to HBM.
+ * hi/lo: padded split waveform from acx_wave_prep.  dft_hi/lo: (n_chunks*128, n_fft) bf16,
+ * chunk c rows [0,64) = real rows of bins [64c, 64c+64), rows [64,128) = imag rows.
+ * mel_hi/lo: (n_chunks*256, 64) bf16, chunk c rows m<224 = melW[64c + k, m] (K-major), rest 0.
+ * out (B, T, n_mels) fp32. */
+ACX_API int acx_frontend_fused(const void* hi, const void* lo, int ld_pad, const void* dft_hi, const void* dft_lo,
+                       const void* mel_hi, const void* mel_lo, int n_chunks, const float* bn_scale,
+                       const float* bn_shift, float* out, int B, int T, int n_fft, int hop, int n_mels,
+                       void* stream);
+
+/* ---- stem: Conv2d(1,96,4x4,s4,pad=(4,0)) + channels_first LayerNorm (CX:688-691, CX:227) ---- */
+/* logmel (B, T, 224) fp32 -> out (B, H0, 56, 96) act_dtype, H0 = (T+4)/4 + 1.
+ * w (16, 96) fp32 = stem weight transposed to (ky*4+kx, cout). */
+ACX_API int acx_stem(const float* logmel, const float* w, const float* bias, const float* ln_w, const float* ln_b,
+             void* out, int B, int T, int n_mels, int act_dtype, void* stream);
+
+/* ---- Block part 1: depthwise 7x7 (pad 3, bias) + channels-last LayerNorm eps 1e-6 (CX:76-78) - */
+/* x (B,H,W,C) -> y (B,H,W,C); w (49, C) act_dtype (dwconv weight transposed), W % 7 == 0. */
+ACX_API int acx_dwconv_ln(const void* x, const void* w, const float* bias, const float* ln_w, const float* ln_b,
+                  void* y, int B, int H, int W, int C, int act_dtype, void* stream);
+
+/* ---- downsample prologue: channels_first LayerNorm + 2x2/s2 patch gather (CX:231-234) ------- */
+/* x (B,H,W,C) -> a (B*(H/2)*(W/2), 4C) with k = (dy*2+dx)*C + c  (the GEMM A operand). */
+ACX_API int acx_ln_patchify(const void* x, const float* ln_w, const float* ln_b, void* a, int B, int H, int W, int C,
+                    int act_dtype, void* stream);
+
+/* ---- GEMMs: out[M,N] = epi(A[M,K] . W[N,K]^T)  (nn.Linear / conv-as-GEMM weight layout) ------ */
+/* bf16 operands, fp32 accumulation in TMEM (tcgen05.mma, TMA-fed).  K % 8 == 0, N % 32 == 0. */
+ACX_API int acx_gemm_bf16(const void* A, const void* W, void* out, int M, int N, int K, int epilogue,
+                  const float* bias, const float* gamma, const void* resid, void* stream);
+/* fp32 SIMT GEMM of the fp32-accurate path.  Row m of A starts at
+ * A + (m / rows_per_batch) * batch_stride + (m % rows_per_batch) * row_stride (elements), which
+ * also expresses the overlapping STFT frames (row_stride = hop). */
+ACX_API int acx_gemm_f32(const float* A, long long batch_stride, int rows_per_batch, int row_stride, const float* W,
+                 float* out, int ldo, int M, int N, int K, int epilogue, const float* bias,
+                 const float* gamma, const float* resid, void* stream);
+
+/* ---- Block part 2, fused: pwconv1 -> GELU -> pwconv2 -> gamma -> +residual (CX:79-86) -------- */
+/* y (M,C) bf16 LN output; x (M,C) bf16 residual stream, updated IN PLACE.
+ * w1 (4C,C), w2 (C,4C) bf16.  The 4C hidden tile lives in TMEM/SMEM only.  C in {96,192}. */
+ACX_API int acx_mlp_fused(const void* y, void* x, const void* w1, const float* b1, const void* w2, const float* b2,
+                  const float* gamma, int M, int C, void* stream);
+
+/* ---- tail: mean over mel, max_t + mean_t, LayerNorm(768), fc 768->527, sigmoid (CX:279-285, 321-325) */
+/* x (B,H,W,C) act_dtype -> scene (B,C) fp32 [post-LN], logits (B,n_cls), probs (B,n_cls). */
+ACX_API int acx_head(const void* x, const float* ln_w, const float* ln_b, const float* fc_w, const float* fc_b,
+             float* scene, float* logits, float* probs, int B, int H, int W, int C, int n_cls, int act_dtype,
+             void* stream);
+
+/* x (B,H,W,C) act_dtype -> out (B,C,H,W) fp32: the layout forward_frame_embeddings returns (CX:399-402). */
+ACX_API int acx_nhwc_to_nchw_f32(const void* x, float* out, int B, int H, int W, int C, int act_dtype, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ACX_H_ */

@@ -1,0 +1,37 @@
+"""TEST INFRASTRUCTURE ONLY -- imports the UNMODIFIED reference model in this container.
+
+`/root/reference` is mounted read-only in the build container only; it does not exist on
+the GPU box.  Nothing under `-m gpu` tests, `smoke()` or `bench.py` may call this at run
+time -- it is used (a) to validate `oracle/convnext_oracle.py` and (b) by
+`oracle/make_golden.py` to generate the committed fixtures in `tests/golden/`.
+"""
+import importlib
+import os
+import sys
+
+REFERENCE_ROOT = os.environ.get("ACX_REFERENCE_ROOT", "/root/reference")
+_SHIM = os.path.join(os.path.dirname(os.path.abspath(__file__)), "torchlibrosa_shim")
+
+
+def reference_available() -> bool:
+    return os.path.isfile(os.path.join(
+        REFERENCE_ROOT, "src", "audioset_convnext_inf", "pytorch", "convnext.py"))
+
+
+def import_reference_convnext():
+    """Return the reference module `audioset_convnext_inf.pytorch.convnext` (unmodified
+    source, /root/reference/src/audioset_convnext_inf/pytorch/convnext.py)."""
+    if not reference_available():
+        raise RuntimeError(f"reference tree not found under {REFERENCE_ROOT}")
+    for p in (os.path.join(REFERENCE_ROOT, "src"), _SHIM):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    return importlib.import_module("audioset_convnext_inf.pytorch.convnext")
+
+
+def build_reference_tiny():
+    """The configuration every reference caller uses (convnext.py:499-505,
+    evaluate_convnext_on_audioset.py:23-29)."""
+    mod = import_reference_convnext()
+    return mod.convnext_tiny(pretrained=False, strict=False, drop_path_rate=0.0,
+                             after_stem_dim=[252, 56], use_speed_perturb=False)
