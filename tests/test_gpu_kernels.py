@@ -1,0 +1,185 @@
+"""GPU (B200): per-kernel parity of libacx (through the C ABI) against the CPU oracle."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from audioset_convnext_inf_b200 import _native as N          # noqa: E402
+from oracle import convnext_oracle as O                       # noqa: E402
+from oracle import weights                                    # noqa: E402
+
+DEV = "cuda:0"
+
+
+def _st():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _adt(dtype):
+    return N.ACX_BF16 if dtype == torch.bfloat16 else N.ACX_F32
+
+
+@pytest.fixture(scope="module")
+def sd():
+    return weights.make_state_dict("parity", 8)
+
+
+def test_device_is_b200():
+    assert N.load().acx_device_ok() == 1, N.last_error()
+
+
+@pytest.mark.parametrize("L", [320000, 1000, 40123])
+def test_wave_prep_reflect_pad_and_split(L):
+    w = weights.make_waveforms(2, n_samples=L, kind="tones", seed=2).to(DEV)
+    ld = (L + 1024 + 7) // 8 * 8
+    ref = F.pad(w[:, None], (512, 512), mode="reflect")[:, 0]
+    pad32 = torch.full((2, ld), 7.0, device=DEV)
+    N.call("acx_wave_prep", w.data_ptr(), pad32.data_ptr(), 0, 2, L, 1024, ld, N.ACX_F32, _st())
+    assert torch.equal(pad32[:, : L + 1024], ref)            # bit-exact copy
+    assert (pad32[:, L + 1024:] == 0).all()
+    hi = torch.empty(2, ld, device=DEV, dtype=torch.bfloat16)
+    lo = torch.empty_like(hi)
+    N.call("acx_wave_prep", w.data_ptr(), hi.data_ptr(), lo.data_ptr(), 2, L, 1024, ld, N.ACX_BF16, _st())
+    assert torch.equal(hi[:, : L + 1024], ref.to(torch.bfloat16))
+    rec = hi.float() + lo.float()
+    assert (rec[:, : L + 1024] - ref).abs().max() <= ref.abs().max() * 2.0 ** -16
+
+
+@pytest.mark.parametrize("epi", [N.EPI_BIAS, N.EPI_BIAS_GELU, N.EPI_BIAS_SCALE_RESID])
+@pytest.mark.parametrize("M,Nn,K", [(300, 192, 96), (1000, 1026, 1024), (130, 96, 384)])
+def test_gemm_f32(M, Nn, K, epi):
+    g = torch.Generator().manual_seed(M + Nn + K + epi)
+    A = torch.randn(M, K, generator=g)
+    W = torch.randn(Nn, K, generator=g) * 0.05
+    bias, gamma, resid = torch.randn(Nn, generator=g), torch.rand(Nn, generator=g), torch.randn(M, Nn, generator=g)
+    ref = A.double() @ W.double().t() + bias.double()
+    if epi == N.EPI_BIAS_GELU:
+        ref = F.gelu(ref)
+    if epi == N.EPI_BIAS_SCALE_RESID:
+        ref = resid.double() + gamma.double() * ref
+    Ad, Wd, bd, gd, rd = (t.to(DEV) for t in (A, W, bias, gamma, resid))
+    out = torch.empty(M, Nn, device=DEV)
+    N.call("acx_gemm_f32", Ad.data_ptr(), 0, M, K, Wd.data_ptr(), out.data_ptr(), Nn, M, Nn, K, epi, bd.data_ptr(),
+           gd.data_ptr(), rd.data_ptr(), _st())
+    assert (out.cpu().double() - ref).abs().max() < 2e-4
+
+
+def test_gemm_f32_overlapping_frames():
+    """STFT framing: row t of clip b starts at b*ld + t*hop (torchlibrosa conv1d stride, CX:298)."""
+    B, L, hop, K = 2, 6400, 320, 1024
+    T = (L - K) // hop + 1
+    wav = torch.randn(B, L)
+    W = torch.randn(64, K) * 0.03
+    frames = wav.unfold(1, K, hop)                            # (B, T, K)
+    ref = frames.double() @ W.double().t()
+    out = torch.empty(B * T, 64, device=DEV)
+    wd, Wd = wav.to(DEV), W.to(DEV)
+    N.call("acx_gemm_f32", wd.data_ptr(), L, T, hop, Wd.data_ptr(), out.data_ptr(), 64, B * T, 64, K, N.EPI_BIAS, 0, 0,
+           0, _st())
+    assert (out.cpu().double().view(B, T, 64) - ref).abs().max() < 1e-4
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_stem(sd, dtype):
+    B, T = 2, 103
+    lm = torch.randn(B, T, 224) * 2
+    ref = O.stem(lm[:, None], sd, torch.float32).permute(0, 2, 3, 1)      # NHWC
+    H0 = ref.shape[1]
+    out = torch.empty(B, H0, 56, 96, device=DEV, dtype=dtype)
+    w = sd["downsample_layers.0.0.weight"].reshape(96, 16).t().contiguous().to(DEV)
+    args = [sd[k].to(DEV) for k in ("downsample_layers.0.0.bias", "downsample_layers.0.1.weight",
+                                    "downsample_layers.0.1.bias")]
+    lmd = lm.to(DEV)
+    N.call("acx_stem", lmd.data_ptr(), w.data_ptr(), args[0].data_ptr(), args[1].data_ptr(), args[2].data_ptr(),
+           out.data_ptr(), B, T, 224, _adt(dtype), _st())
+    tol = 1e-4 if dtype == torch.float32 else 3e-2
+    assert (out.float().cpu() - ref).abs().max() < tol
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("stage,H", [(0, 13), (1, 9), (2, 7), (3, 5), (3, 31)])
+def test_dwconv_ln(sd, stage, H, dtype):
+    C, Wd = O.DIMS[stage], 56 >> stage
+    B = 2
+    p = f"stages.{stage}.1."
+    g = torch.Generator().manual_seed(stage * 100 + H)
+    x = torch.randn(B, H, Wd, C, generator=g)
+    xq = x.to(dtype)
+    sdq = dict(sd)
+    sdq[p + "dwconv.weight"] = sd[p + "dwconv.weight"].to(dtype).float()  # kernel holds taps in act dtype
+    ref = O.block_dwconv_ln(xq.float().permute(0, 3, 1, 2), sdq, p, torch.float32)
+    y = torch.empty(B, H, Wd, C, device=DEV, dtype=dtype)
+    w = sd[p + "dwconv.weight"].reshape(C, 49).t().to(dtype).contiguous().to(DEV)
+    b, lw, lb = (sd[p + k].to(DEV) for k in ("dwconv.bias", "norm.weight", "norm.bias"))
+    xd = xq.to(DEV)
+    N.call("acx_dwconv_ln", xd.data_ptr(), w.data_ptr(), b.data_ptr(), lw.data_ptr(), lb.data_ptr(), y.data_ptr(), B, H,
+           Wd, C, _adt(dtype), _st())
+    err = (y.float().cpu() - ref).abs().max().item()
+    assert err < (2e-4 if dtype == torch.float32 else 4e-2), err
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("stage,H", [(0, 10), (1, 7), (2, 63)])
+def test_ln_patchify_then_gemm_is_downsample(sd, stage, H, dtype):
+    C, Wd = O.DIMS[stage], 56 >> stage
+    B = 2
+    i = stage + 1
+    x = torch.randn(B, H, Wd, C, generator=torch.Generator().manual_seed(i))
+    xq = x.to(dtype)
+    ref = O.downsample(xq.float().permute(0, 3, 1, 2), sd, i, torch.float32).permute(0, 2, 3, 1)   # (B,Ho,Wo,2C)
+    Ho, Wo = H // 2, Wd // 2
+    a = torch.empty(B * Ho * Wo, 4 * C, device=DEV, dtype=dtype)
+    lw, lb = sd[f"downsample_layers.{i}.0.weight"].to(DEV), sd[f"downsample_layers.{i}.0.bias"].to(DEV)
+    xd = xq.to(DEV)
+    N.call("acx_ln_patchify", xd.data_ptr(), lw.data_ptr(), lb.data_ptr(), a.data_ptr(), B, H, Wd, C, _adt(dtype), _st())
+    # patch matrix itself == LayerNorm'd pixels gathered (dy, dx, c)
+    ln = O.layernorm_cf(xq.float().permute(0, 3, 1, 2), sd[f"downsample_layers.{i}.0.weight"],
+                        sd[f"downsample_layers.{i}.0.bias"]).permute(0, 2, 3, 1)[:, : Ho * 2, : Wo * 2]
+    pat = ln.reshape(B, Ho, 2, Wo, 2, C).permute(0, 1, 3, 2, 4, 5).reshape(B * Ho * Wo, 4 * C)
+    assert (a.float().cpu() - pat).abs().max() < (1e-4 if dtype == torch.float32 else 4e-2)
+    w = sd[f"downsample_layers.{i}.1.weight"].permute(0, 2, 3, 1).reshape(2 * C, 4 * C).contiguous()
+    out = (a.float().cpu() @ w.t() + sd[f"downsample_layers.{i}.1.bias"]).view(B, Ho, Wo, 2 * C)
+    assert (out - ref).abs().max() < (1e-3 if dtype == torch.float32 else 6e-2)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("H", [31, 9])
+def test_head_and_frame_layout(sd, H, dtype):
+    B = 3
+    x = torch.randn(B, H, 7, 768, generator=torch.Generator().manual_seed(H))
+    xq = x.to(dtype)
+    scene_ref, logits_ref, probs_ref = O.pool_head(xq.float().permute(0, 3, 1, 2), sd, torch.float32)
+    xd = xq.to(DEV)
+    scene = torch.empty(B, 768, device=DEV)
+    logits = torch.empty(B, 527, device=DEV)
+    probs = torch.empty(B, 527, device=DEV)
+    t = [sd[k].to(DEV) for k in ("norm.weight", "norm.bias", "head_audioset.weight", "head_audioset.bias")]
+    N.call("acx_head", xd.data_ptr(), t[0].data_ptr(), t[1].data_ptr(), t[2].data_ptr(), t[3].data_ptr(),
+           scene.data_ptr(), logits.data_ptr(), probs.data_ptr(), B, H, 7, 768, 527, _adt(dtype), _st())
+    assert (scene.cpu() - scene_ref).abs().max() < 1e-4
+    assert (logits.cpu() - logits_ref).abs().max() < 2e-4
+    assert (probs.cpu() - probs_ref).abs().max() < 1e-4
+    frame = torch.empty(B, 768, H, 7, device=DEV)
+    N.call("acx_nhwc_to_nchw_f32", xd.data_ptr(), frame.data_ptr(), B, H, 7, 768, _adt(dtype), _st())
+    assert torch.equal(frame.cpu(), xq.float().permute(0, 3, 1, 2))
+
+
+def test_frontend_fp32_path_logmel(sd):
+    """SIMT front end (fp32-accurate mode) vs the oracle's torchlibrosa restatement (CX:298-306)."""
+    import audioset_convnext_inf_b200 as acx
+    m = acx.convnext_tiny(drop_path_rate=0.0, after_stem_dim=[252, 56])
+    m.load_state_dict(sd)
+    m = m.to(DEV).eval().set_precision("fp32")
+    for kind in ("noise", "tones"):
+        w = weights.make_waveforms(2, n_samples=64000, kind=kind, seed=4)
+        ref = O.frontend(w, sd, torch.float32)
+        ref64 = O.frontend(w, sd, torch.float64)
+        got = m.forward_logmel(w.to(DEV)).cpu()
+        err = (got - ref).abs()
+        err64 = (got.double() - ref64).abs().max().item()
+        ref_err64 = (ref.double() - ref64).abs().max().item()
+        print(f"[{kind}] logmel_bn |ours-ref| max {err.max():.3e} mean {err.mean():.3e}; vs fp64: ours {err64:.3e} ref {ref_err64:.3e}")
+        # bn0 scales dB by ~1/20: 1e-3 dB abs -> 5e-5 normalised; allow the reference's own fp32 noise
+        assert err64 < max(3 * ref_err64, 1e-4)

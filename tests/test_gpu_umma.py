@@ -1,0 +1,89 @@
+"""GPU (B200): the tcgen05 / TMA GEMM (acx_gemm_bf16) against fp64 matmul of the same bf16 operands
+and against the SIMT fp32 GEMM of the same library."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from audioset_convnext_inf_b200 import _native as N          # noqa: E402
+
+DEV = "cuda:0"
+
+SHAPES = [
+    # (M, N, K)  -- every (BN, K-tail, M-tail) combination the trunk uses
+    (128, 96, 64), (128, 128, 64), (256, 256, 128), (300, 192, 96),
+    (14112, 384, 96), (14112, 96, 384), (3528, 768, 192), (3528, 192, 768),
+    (882, 1536, 384), (882, 384, 1536), (434, 3072, 768), (434, 768, 3072),
+    (7056, 192, 384), (1764, 384, 768), (434, 768, 1536),
+]
+
+
+def _run(M, Nn, K, epi, seed=0):
+    g = torch.Generator().manual_seed(seed + M + 3 * Nn + 7 * K)
+    A = (torch.randn(M, K, generator=g)).to(torch.bfloat16)
+    W = (torch.randn(Nn, K, generator=g) * (1.0 / K ** 0.5)).to(torch.bfloat16)
+    bias = torch.randn(Nn, generator=g) * 0.1
+    gamma = torch.rand(Nn, generator=g)
+    resid = torch.randn(M, Nn, generator=g).to(torch.bfloat16)
+    Ad, Wd, bd, gd, rd = (t.to(DEV) for t in (A, W, bias, gamma, resid))
+    ref = (Ad.double() @ Wd.double().t()) + bd.double()
+    if epi == N.EPI_BIAS_GELU:
+        ref = F.gelu(ref)
+    if epi == N.EPI_BIAS_SCALE_RESID:
+        ref = rd.double() + gd.double() * ref
+    out = torch.full((M, Nn), float("nan"), device=DEV, dtype=torch.bfloat16)
+    st = torch.cuda.current_stream().cuda_stream
+    N.call("acx_gemm_bf16", Ad.data_ptr(), Wd.data_ptr(), out.data_ptr(), M, Nn, K, epi, bd.data_ptr(), gd.data_ptr(),
+           rd.data_ptr(), st)
+    torch.cuda.synchronize()
+    return out.double(), ref
+
+
+@pytest.mark.parametrize("M,Nn,K", SHAPES)
+def test_umma_gemm_bias(M, Nn, K):
+    out, ref = _run(M, Nn, K, N.EPI_BIAS)
+    assert torch.isfinite(out).all()
+    err = (out - ref).abs().max().item()
+    assert err < 0.02 + 0.01 * ref.abs().max().item(), err   # bf16 output rounding
+
+
+@pytest.mark.parametrize("M,Nn,K", [(14112, 384, 96), (882, 1536, 384), (434, 3072, 768), (300, 192, 96)])
+def test_umma_gemm_gelu(M, Nn, K):
+    out, ref = _run(M, Nn, K, N.EPI_BIAS_GELU)
+    err = (out - ref).abs().max().item()
+    assert err < 0.02 + 0.01 * ref.abs().max().item(), err
+
+
+@pytest.mark.parametrize("M,Nn,K", [(14112, 96, 384), (3528, 192, 768), (882, 384, 1536), (434, 768, 3072)])
+def test_umma_gemm_scale_residual_in_place(M, Nn, K):
+    out, ref = _run(M, Nn, K, N.EPI_BIAS_SCALE_RESID)
+    err = (out - ref).abs().max().item()
+    assert err < 0.03 + 0.01 * ref.abs().max().item(), err
+    # in-place form used by the engine: out aliases resid
+    g = torch.Generator().manual_seed(5)
+    A = torch.randn(M, K, generator=g).to(torch.bfloat16).to(DEV)
+    W = (torch.randn(Nn, K, generator=g) / K ** 0.5).to(torch.bfloat16).to(DEV)
+    bias = torch.zeros(Nn, device=DEV)
+    gamma = torch.ones(Nn, device=DEV)
+    x = torch.randn(M, Nn, generator=g).to(torch.bfloat16).to(DEV)
+    ref = x.double() + A.double() @ W.double().t()
+    N.call("acx_gemm_bf16", A.data_ptr(), W.data_ptr(), x.data_ptr(), M, Nn, K, N.EPI_BIAS_SCALE_RESID,
+           bias.data_ptr(), gamma.data_ptr(), x.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    assert (x.double() - ref).abs().max().item() < 0.03 + 0.01 * ref.abs().max().item()
+
+
+def test_umma_gemm_many_tiles_persistent_loop():
+    """More tiles than SMs x 2 accumulators: exercises the phase bookkeeping of both pipelines."""
+    out, ref = _run(128 * 700, 192, 192, N.EPI_BIAS)
+    assert (out - ref).abs().max().item() < 0.02 + 0.01 * ref.abs().max().item()
+
+
+def test_umma_rejects_bad_arguments():
+    lib = N.load()
+    assert lib.acx_gemm_bf16(0, 0, 0, 16, 96, 64, 0, 0, 0, 0, 0) != 0
+    assert "null" in N.last_error()
+    t = torch.zeros(128, 100, device=DEV, dtype=torch.bfloat16)
+    b = torch.zeros(100, device=DEV)
+    rc = lib.acx_gemm_bf16(t.data_ptr(), t.data_ptr(), t.data_ptr(), 128, 100, 64, 0, b.data_ptr(), 0, 0, 0)
+    assert rc != 0 and "multiple" in N.last_error()

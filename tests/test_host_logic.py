@@ -1,0 +1,137 @@
+"""CPU: host-side logic of the product package and the C-ABI library surface (no compute calls)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import audioset_convnext_inf_b200 as acx
+from audioset_convnext_inf_b200 import _native
+from audioset_convnext_inf_b200.engine import PackedWeights, out_time_dims
+from oracle import convnext_oracle as O
+from oracle import weights
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _tiny():
+    return acx.convnext_tiny(pretrained=False, strict=False, drop_path_rate=0.0, after_stem_dim=[252, 56])
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "acx.h")).read()
+    declared = set(re.findall(r"ACX_API\s+[\w\s\*]+?\b(acx_\w+)\s*\(", header))
+    assert len(declared) >= 14
+    lib = ctypes.CDLL(_native.load()._name)
+    missing = [n for n in sorted(declared) if not hasattr(lib, n)]
+    assert not missing, f"libacx.so does not export: {missing}"
+    assert set(_native.SIGNATURES) == declared, set(_native.SIGNATURES) ^ declared
+    assert lib.acx_version() == 100
+
+
+def test_module_surface_matches_reference_contract():
+    m = _tiny()
+    assert sum(p.numel() for p in m.parameters() if p.requires_grad) == 28222767      # README.md:49
+    sd = m.state_dict()
+    ref = weights.make_state_dict("init", 0)
+    assert len(sd) == 190 and set(sd) == set(ref)
+    for k in ref:
+        assert sd[k].shape == ref[k].shape and sd[k].dtype == ref[k].dtype, k
+    # frozen front-end tensors are bit-identical to torchlibrosa's constants
+    for k in ("spectrogram_extractor.stft.conv_real.weight", "spectrogram_extractor.stft.conv_imag.weight",
+              "logmel_extractor.melW"):
+        assert torch.equal(sd[k], ref[k]) and not dict(m.named_parameters())[k].requires_grad
+    for name in ("forward", "forward_scene_embeddings", "forward_frame_embeddings", "from_pretrained"):
+        assert callable(getattr(acx.ConvNeXt, name))
+
+
+def test_no_cpu_fallback_and_training_mode_raise():
+    m = _tiny()
+    with pytest.raises(RuntimeError, match="eval"):
+        m(torch.zeros(1, 32000))
+    m.eval()
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        m(torch.zeros(1, 32000))
+
+
+def test_unsupported_configs_raise_explicitly():
+    with pytest.raises(ValueError):
+        acx.convnext_tiny(after_stem_dim=[7, 7], drop_path_rate=0.0)
+    with pytest.raises(NotImplementedError):
+        acx.convnext_tiny(after_stem_dim=[56], drop_path_rate=0.0)
+    with pytest.raises(NotImplementedError):
+        acx.convnext_tiny(after_stem_dim=[252, 56])          # default drop_path_rate=0.1 is training-only
+    with pytest.raises(NotImplementedError):
+        acx.LayerNorm(8, data_format="nope")
+
+
+def test_checkpoint_round_trips(tmp_path):
+    from safetensors.torch import save_model
+    sd = weights.make_state_dict("parity", 3)
+    m = _tiny()
+    m.load_state_dict(sd, strict=True)
+    st_path = str(tmp_path / "model.safetensors")
+    save_model(m, st_path)                                   # convert_pytorch_ckpt_to_safetensors.py:18
+    m2 = acx.ConvNeXt.from_pretrained(st_path)
+    assert m2.training                                       # like the reference: caller must .eval()
+    for k, v in m2.state_dict().items():
+        assert torch.equal(v, sd[k]), k
+    pth = str(tmp_path / "ckpt.pth")
+    torch.save({"model": sd}, pth)                           # evaluate_convnext_on_audioset.py:36-38
+    m3 = acx.ConvNeXt.from_pretrained(pth)
+    for k, v in m3.state_dict().items():
+        assert torch.equal(v, sd[k]), k
+
+
+def test_packed_weights_layouts():
+    sd = weights.make_state_dict("parity", 8)
+    pw = PackedWeights(sd, torch.device("cpu"), "bf16")
+    # mel band table reproduces the dense filterbank
+    melW = sd["logmel_extractor.melW"]
+    dense = torch.zeros_like(melW)
+    for m in range(224):
+        lo, hi = int(pw.mel_lo[m]), int(pw.mel_hi[m])
+        dense[lo:hi, m] = pw.melT[m, lo:hi]
+    assert torch.equal(dense, melW)
+    assert pw.n_chunks == 7                                  # bins 2..447 carry all 884 non-zeros
+    # split-bf16 DFT: hi + lo reproduces fp32 to ~2^-17 relative
+    re = sd["spectrogram_extractor.stft.conv_real.weight"][:448, 0]
+    chunks = (pw.dft_hi.float() + pw.dft_lo.float()).view(7, 2, 64, 1024)
+    assert (chunks[:, 0].reshape(448, 1024) - re).abs().max() < 2e-5
+    # mel chunks: K-major (mel, bin) tiles
+    mel = (pw.melc_hi.float() + pw.melc_lo.float()).view(7, 256, 64)
+    assert (mel[:, :224].permute(0, 2, 1).reshape(448, 224) - melW[:448]).abs().max() < 1e-6
+    assert mel[:, 224:].abs().max() == 0
+    # downsample conv as GEMM over (dy, dx, cin) patches
+    w = sd["downsample_layers.1.1.weight"]
+    x = torch.randn(1, 96, 4, 6)
+    ref = torch.nn.functional.conv2d(x, w, stride=2)
+    patches = x.permute(0, 2, 3, 1).reshape(1, 2, 2, 3, 2, 96).permute(0, 1, 3, 2, 4, 5).reshape(6, 384)
+    got = (patches @ pw.ds[0]["w"].float().t()).reshape(1, 2, 3, 192).permute(0, 3, 1, 2)
+    assert (got - ref).abs().max() < 0.05                    # bf16-rounded weights
+    # dwconv taps transposed to (49, C)
+    assert torch.equal(pw.blocks[0][0]["dw_w"].float().t().reshape(96, 1, 7, 7),
+                       sd["stages.0.0.dwconv.weight"].to(torch.bfloat16).float())
+
+
+@pytest.mark.parametrize("L", [320000, 96123, 960000, 32000])
+def test_out_time_dims_match_oracle_shapes(L):
+    sd = weights.make_state_dict("init", 0)
+    T, hs = out_time_dims(L)
+    lm = torch.zeros(1, 1, T, 224)
+    x = O.stem(lm, sd, torch.float32)
+    assert x.shape[2:] == (hs[0], 56)
+    assert T == L // 320 + 1
+    assert hs == [hs[0], hs[0] // 2, hs[0] // 4, hs[0] // 8] or hs[3] == ((hs[0] // 2) // 2) // 2
+
+
+def test_gelu_fit_against_exact_erf():
+    """The tensor-core epilogue's tanh-form GELU (gemm_umma.cu::gelu_fast) vs nn.GELU()."""
+    x = torch.linspace(-60, 60, 1200001)
+    x2 = torch.clamp(x * x, max=50.0)
+    inner = x * (7.97507884e-01 + x2 * (3.70056460e-02 + x2 * -3.51516788e-04))
+    fast = 0.5 * x * (1 + torch.tanh(inner))
+    exact = torch.nn.functional.gelu(x.double())
+    assert (fast.double() - exact).abs().max() < 4e-5
