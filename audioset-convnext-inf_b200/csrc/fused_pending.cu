@@ -8,8 +8,3 @@ int acx_mlp_fused(const void*, void*, const void*, const float*, const void*, co
   return ACX_ERR_UNSUPPORTED;
 }
 }
-extern "C" int acx_frontend_fused(const void*, const void*, int, const void*, const void*, const void*, const void*, int,
-                                  const float*, const float*, float*, int, int, int, int, int, void*) {
-  set_error("acx_frontend_fused: not available in this build");
-  return ACX_ERR_UNSUPPORTED;
-}

@@ -127,11 +127,11 @@ __global__ void __launch_bounds__(256) stem_kernel(const float* __restrict__ log
 // The 49 taps of the thread's two channels live in registers for the whole block lifetime; per
 // input row the thread loads 13 channel-pairs and issues 98 FMAs (7.5 FMA per load).
 // LayerNorm: two-pass; per-pixel partial sums are reduce-scattered inside each 16-lane group
-// (8 shuffles for 7 pixels) and combined across groups with shared-memory atomics.
+// (8 shuffles for 7 pixels) and combined across groups through shared memory in a FIXED order.
 // =============================================================================================
-template <int S>
-__device__ __forceinline__ void strip_reduce_add(float (&v)[8], float* red /*[8] of this strip*/, int lane) {
-  // reduce-scatter over lanes differing in bits 3,2,1 of the 16-lane group, then bit 0.
+// Per-pixel sums of 7 values over the 16 lanes of a half-warp: reduce-scatter (8 shuffles instead of 28).
+// On return lanes with (lane & 1) == 0 hold the total of pixel p = bits (3,2,1) of the lane in v[0].
+__device__ __forceinline__ void halfwarp_reduce7(float (&v)[8], int lane) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const bool up = lane & 8;
@@ -153,9 +153,37 @@ __device__ __forceinline__ void strip_reduce_add(float (&v)[8], float* red /*[8]
     v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
   }
   v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
-  if ((lane & 1) == 0) {
-    const int p = ((lane & 8) ? 4 : 0) + ((lane & 4) ? 2 : 0) + ((lane & 2) ? 1 : 0);
-    if (p < 7) atomicAdd(red + p, v[0]);
+}
+
+// Block-level, ORDER-FIXED reduction of the 7 per-pixel values of a strip over all its C/2 threads, so a clip's
+// result is bit-identical whatever else is in the batch (no atomics).  G = C/32 half-warp groups per strip.
+// Returns the totals in tot[0..6].  Uses two __syncthreads (three when G > 6).
+template <int G>
+__device__ __forceinline__ void strip_allreduce7(float (&v)[8], float (&tot)[7], float* part /*[G][8]*/,
+                                                 float* sums /*[8]*/, int lane, int grp, int cp) {
+  halfwarp_reduce7(v, lane);
+  if ((lane & 1) == 0) part[grp * 8 + ((lane >> 1) & 7)] = v[0];
+  __syncthreads();
+  if (G <= 6) {
+#pragma unroll
+    for (int p = 0; p < 7; ++p) {
+      float t = part[p];
+#pragma unroll
+      for (int g = 1; g < G; ++g) t += part[g * 8 + p];
+      tot[p] = t;
+    }
+    __syncthreads();  // part[] may be rewritten by the next reduction
+  } else {
+    if (cp < 7) {
+      float t = part[cp];
+#pragma unroll
+      for (int g = 1; g < G; ++g) t += part[g * 8 + cp];
+      sums[cp] = t;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int p = 0; p < 7; ++p) tot[p] = sums[p];
+    __syncthreads();
   }
 }
 
@@ -167,11 +195,15 @@ __global__ void __launch_bounds__(S* C / 2)
   using P = Pair<T>;
   using PT = typename P::type;
   constexpr int TPS = C / 2;  // threads per strip
-  __shared__ float red[2][2][S][8];  // [buffer][sum | sumsq][strip][pixel]
+  constexpr int G = C / 32;   // half-warp groups per strip
+  static_assert((S * TPS) % 32 == 0, "block must be whole warps (full-mask shuffles)");
+  __shared__ float part[S][G][8];
+  __shared__ float sums[S][8];
   const int tid = threadIdx.x;
   const int lane = tid & 31;
   const int cp = tid % TPS;
   const int s = tid / TPS;
+  const int grp = cp >> 4;
   const int strip = blockIdx.x * S + s;
   const int w0 = strip * 7;
   const int b = blockIdx.z;
@@ -179,20 +211,16 @@ __global__ void __launch_bounds__(S* C / 2)
   const PT* xp = reinterpret_cast<const PT*>(x) + (size_t)b * H * W * TPS;
   PT* yp = reinterpret_cast<PT*>(y) + (size_t)b * H * W * TPS;
 
-  for (int i = tid; i < 2 * 2 * S * 8; i += S * TPS) (&red[0][0][0][0])[i] = 0.f;
-
   PT wr[49];
 #pragma unroll
   for (int k = 0; k < 49; ++k) wr[k] = reinterpret_cast<const PT*>(w)[k * TPS + cp];
   const float2 bs = make_float2(bias[2 * cp], bias[2 * cp + 1]);
   const float2 gw = make_float2(ln_w[2 * cp], ln_w[2 * cp + 1]);
   const float2 gb = make_float2(ln_b[2 * cp], ln_b[2 * cp + 1]);
-  __syncthreads();
 
   for (int r = 0; r < ROWS; ++r) {
     const int h = h_begin + r;
     if (h >= H) break;  // block-uniform
-    const int buf = r & 1;
     float2 acc[7];
 #pragma unroll
     for (int p = 0; p < 7; ++p) acc[p] = bs;
@@ -217,30 +245,25 @@ __global__ void __launch_bounds__(S* C / 2)
         }
       }
     }
-    // ---- LayerNorm over C (two-pass, fp32) -------------------------------------------------
-    float v[8];
+    // ---- LayerNorm over C (two-pass, fp32, fixed summation order) ----------------------------
+    float v[8], tot[7];
 #pragma unroll
     for (int p = 0; p < 7; ++p) v[p] = acc[p].x + acc[p].y;
     v[7] = 0.f;
-    strip_reduce_add<S>(v, &red[buf][0][s][0], lane);
-    __syncthreads();
-    // safe to clear the other buffer now: its readers all passed this barrier
-    for (int i = tid; i < 2 * S * 8; i += S * TPS) (&red[buf ^ 1][0][0][0])[i] = 0.f;
-    float mean[7];
+    strip_allreduce7<G>(v, tot, &part[s][0][0], &sums[s][0], lane, grp, cp);
 #pragma unroll
     for (int p = 0; p < 7; ++p) {
-      mean[p] = red[buf][0][s][p] * (1.0f / C);
-      acc[p].x -= mean[p];
-      acc[p].y -= mean[p];
+      const float mean = tot[p] * (1.0f / C);
+      acc[p].x -= mean;
+      acc[p].y -= mean;
       v[p] = acc[p].x * acc[p].x + acc[p].y * acc[p].y;
     }
     v[7] = 0.f;
-    strip_reduce_add<S>(v, &red[buf][1][s][0], lane);
-    __syncthreads();
+    strip_allreduce7<G>(v, tot, &part[s][0][0], &sums[s][0], lane, grp, cp);
     PT* orow = yp + ((size_t)h * W + w0) * TPS + cp;
 #pragma unroll
     for (int p = 0; p < 7; ++p) {
-      const float rstd = rsqrtf(red[buf][1][s][p] * (1.0f / C) + 1e-6f);
+      const float rstd = rsqrtf(tot[p] * (1.0f / C) + 1e-6f);
       orow[(size_t)p * TPS] = P::pack(acc[p].x * rstd * gw.x + gb.x, acc[p].y * rstd * gw.y + gb.y);
     }
   }
@@ -436,7 +459,8 @@ static int dispatch_dwconv(const void* x, const void* w, const float* bias, cons
     case 96:
       if (strips % 4 == 0) return launch_dwconv<T, 96, 4, 4>(x, w, bias, ln_w, ln_b, y, B, H, W, st);
       if (strips % 2 == 0) return launch_dwconv<T, 96, 2, 4>(x, w, bias, ln_w, ln_b, y, B, H, W, st);
-      return launch_dwconv<T, 96, 1, 4>(x, w, bias, ln_w, ln_b, y, B, H, W, st);
+      set_error("dwconv_ln: C=96 needs an even number of 7-pixel strips per row (W=%d)", W);
+      return ACX_ERR_UNSUPPORTED;
     case 192:
       if (strips % 2 == 0) return launch_dwconv<T, 192, 2, 4>(x, w, bias, ln_w, ln_b, y, B, H, W, st);
       return launch_dwconv<T, 192, 1, 4>(x, w, bias, ln_w, ln_b, y, B, H, W, st);

@@ -152,6 +152,7 @@ class Engine:
         if precision == "fp32":
             self.frontend, self.mlp = "simt", "gemm"
         self._ws = {}
+        self._prof = None
 
     # ---- workspace ------------------------------------------------------------------------------
     def _workspace(self, n, L):
@@ -162,7 +163,7 @@ class Engine:
         T, hs = out_time_dims(L)
         dev = self.device
         adt = self.w.act_dtype
-        ld_pad = (L + N_FFT + 7) // 8 * 8
+        ld_pad = (max(L + N_FFT, HOP * (T + 3)) + 7) // 8 * 8     # fused front end reads whole hops
         ws = dict(T=T, hs=hs, ld_pad=ld_pad)
         if self.frontend == "fused":
             ws["wav_hi"] = torch.empty(n, ld_pad, device=dev, dtype=torch.bfloat16)
@@ -179,44 +180,67 @@ class Engine:
         self._ws[key] = ws
         return ws
 
+    # ---- per-kernel device timing (tools/time_stages.py, bench.py roofline leg) ------------------------
+    def _call(self, tag, name, *args):
+        if self._prof is None:
+            N.call(name, *args)
+            return
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        N.call(name, *args)
+        e1.record()
+        self._prof.append((tag, e0, e1))
+
+    def profile(self, wave, want=("logits",)):
+        """Run once with a CUDA-event pair around every kernel launch (serialised on the current
+        stream); returns [(tag, milliseconds)] in launch order."""
+        self._prof = []
+        try:
+            self.run(wave, want)
+            torch.cuda.synchronize(self.device)
+            return [(tag, e0.elapsed_time(e1)) for tag, e0, e1 in self._prof]
+        finally:
+            self._prof = None
+
     # ---- stages (each is one libacx call) ----------------------------------------------------------
     def _frontend(self, wave, ws, n, L, st):
         w = self.w
         T, ld_pad = ws["T"], ws["ld_pad"]
         if self.frontend == "fused":
-            N.call("acx_wave_prep", wave.data_ptr(), ws["wav_hi"].data_ptr(), ws["wav_lo"].data_ptr(), n, L, N_FFT,
+            self._call("wave_prep", "acx_wave_prep", wave.data_ptr(), ws["wav_hi"].data_ptr(), ws["wav_lo"].data_ptr(), n, L, N_FFT,
                    ld_pad, N.ACX_BF16, st)
-            N.call("acx_frontend_fused", ws["wav_hi"].data_ptr(), ws["wav_lo"].data_ptr(), ld_pad,
+            self._call("frontend_fused", "acx_frontend_fused", ws["wav_hi"].data_ptr(), ws["wav_lo"].data_ptr(), ld_pad,
                    w.dft_hi.data_ptr(), w.dft_lo.data_ptr(), w.melc_hi.data_ptr(), w.melc_lo.data_ptr(), w.n_chunks,
                    w.bn_scale.data_ptr(), w.bn_shift.data_ptr(), ws["logmel"].data_ptr(), n, T, N_FFT, HOP, N_MELS, st)
         else:
-            N.call("acx_wave_prep", wave.data_ptr(), ws["wav_pad"].data_ptr(), 0, n, L, N_FFT, ld_pad, N.ACX_F32, st)
-            N.call("acx_gemm_f32", ws["wav_pad"].data_ptr(), ld_pad, T, HOP, w.dft_f32.data_ptr(),
+            self._call("wave_prep", "acx_wave_prep", wave.data_ptr(), ws["wav_pad"].data_ptr(), 0, n, L, N_FFT, ld_pad, N.ACX_F32, st)
+            self._call("dft_simt", "acx_gemm_f32", ws["wav_pad"].data_ptr(), ld_pad, T, HOP, w.dft_f32.data_ptr(),
                    ws["spec"].data_ptr(), 2 * N_BINS, n * T, 2 * N_BINS, N_FFT, N.EPI_BIAS, 0, 0, 0, st)
-            N.call("acx_power_mel_log", ws["spec"].data_ptr(), 2 * N_BINS, N_BINS, w.melT.data_ptr(),
+            self._call("power_mel_log", "acx_power_mel_log", ws["spec"].data_ptr(), 2 * N_BINS, N_BINS, w.melT.data_ptr(),
                    w.mel_lo.data_ptr(), w.mel_hi.data_ptr(), w.bn_scale.data_ptr(), w.bn_shift.data_ptr(),
                    ws["logmel"].data_ptr(), n * T, N_MELS, st)
 
     def _gemm(self, a, wt, out, M, Nn, K, epi, bias, gamma, resid, st):
+        tag = f"{('ds', 'pw1_gelu', 'pw2_resid')[epi]}_k{K}_n{Nn}"
         if self.precision == "bf16":
-            N.call("acx_gemm_bf16", a, wt, out, M, Nn, K, epi, bias, gamma, resid, st)
+            self._call(tag, "acx_gemm_bf16", a, wt, out, M, Nn, K, epi, bias, gamma, resid, st)
         else:
-            N.call("acx_gemm_f32", a, M * K, M, K, wt, out, Nn, M, Nn, K, epi, bias, gamma, resid, st)
+            self._call(tag, "acx_gemm_f32", a, M * K, M, K, wt, out, Nn, M, Nn, K, epi, bias, gamma, resid, st)
 
     def _trunk(self, ws, n, st):
         w = self.w
         x, y, hid = ws["x"].data_ptr(), ws["y"].data_ptr(), ws["hid"].data_ptr()
-        N.call("acx_stem", ws["logmel"].data_ptr(), w.stem_w.data_ptr(), w.stem_b.data_ptr(),
+        self._call("stem", "acx_stem", ws["logmel"].data_ptr(), w.stem_w.data_ptr(), w.stem_b.data_ptr(),
                w.stem_ln_w.data_ptr(), w.stem_ln_b.data_ptr(), x, n, ws["T"], N_MELS, self.adt, st)
         Wd = 56
         for s in range(4):
             C, H = DIMS[s], ws["hs"][s]
             M = n * H * Wd
             for blk in w.blocks[s]:
-                N.call("acx_dwconv_ln", x, blk["dw_w"].data_ptr(), blk["dw_b"].data_ptr(), blk["ln_w"].data_ptr(),
+                self._call(f"dwconv_ln_c{C}", "acx_dwconv_ln", x, blk["dw_w"].data_ptr(), blk["dw_b"].data_ptr(), blk["ln_w"].data_ptr(),
                        blk["ln_b"].data_ptr(), y, n, H, Wd, C, self.adt, st)
                 if self.mlp == "fused" and C in (96, 192):
-                    N.call("acx_mlp_fused", y, x, blk["w1"].data_ptr(), blk["b1"].data_ptr(), blk["w2"].data_ptr(),
+                    self._call(f"mlp_fused_c{C}", "acx_mlp_fused", y, x, blk["w1"].data_ptr(), blk["b1"].data_ptr(), blk["w2"].data_ptr(),
                            blk["b2"].data_ptr(), blk["gamma"].data_ptr(), M, C, st)
                 else:
                     self._gemm(y, blk["w1"].data_ptr(), hid, M, 4 * C, C, N.EPI_BIAS_GELU, blk["b1"].data_ptr(), 0, 0, st)
@@ -224,7 +248,7 @@ class Engine:
                                blk["b2"].data_ptr(), blk["gamma"].data_ptr(), x, st)
             if s < 3:
                 d = w.ds[s]
-                N.call("acx_ln_patchify", x, d["ln_w"].data_ptr(), d["ln_b"].data_ptr(), y, n, H, Wd, C, self.adt, st)
+                self._call(f"ln_patchify_c{C}", "acx_ln_patchify", x, d["ln_w"].data_ptr(), d["ln_b"].data_ptr(), y, n, H, Wd, C, self.adt, st)
                 Wd //= 2
                 Mo = n * ws["hs"][s + 1] * Wd
                 self._gemm(y, d["w"].data_ptr(), x, Mo, 2 * C, 4 * C, N.EPI_BIAS, d["b"].data_ptr(), 0, 0, st)
@@ -264,9 +288,9 @@ class Engine:
                 x = ws["x"].data_ptr()
                 if need_head:
                     w = self.w
-                    N.call("acx_head", x, w.norm_w.data_ptr(), w.norm_b.data_ptr(), w.fc_w.data_ptr(),
+                    self._call("head", "acx_head", x, w.norm_w.data_ptr(), w.norm_b.data_ptr(), w.fc_w.data_ptr(),
                            w.fc_b.data_ptr(), out["scene"][b0:].data_ptr(), out["logits"][b0:].data_ptr(),
                            out["probs"][b0:].data_ptr(), n, hs[3], 7, DIMS[3], N_CLASSES, self.adt, st)
                 if "frame" in want:
-                    N.call("acx_nhwc_to_nchw_f32", x, out["frame"][b0:].data_ptr(), n, hs[3], 7, DIMS[3], self.adt, st)
+                    self._call("frame_nchw", "acx_nhwc_to_nchw_f32", x, out["frame"][b0:].data_ptr(), n, hs[3], 7, DIMS[3], self.adt, st)
         return out

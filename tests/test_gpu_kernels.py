@@ -183,3 +183,28 @@ def test_frontend_fp32_path_logmel(sd):
         print(f"[{kind}] logmel_bn |ours-ref| max {err.max():.3e} mean {err.mean():.3e}; vs fp64: ours {err64:.3e} ref {ref_err64:.3e}")
         # bn0 scales dB by ~1/20: 1e-3 dB abs -> 5e-5 normalised; allow the reference's own fp32 noise
         assert err64 < max(3 * ref_err64, 1e-4)
+
+
+@pytest.mark.parametrize("kind,L", [("noise", 64000), ("tones", 64000), ("tones", 320000)])
+def test_frontend_fused_logmel(sd, kind, L):
+    """tcgen05 front end (split-bf16 x3 DFT and mel GEMMs) vs the oracle's torchlibrosa restatement.
+    Metrics per SURVEY.md Appendix C; values are in bn0-normalised units (1 unit ~ 20 dB here)."""
+    import audioset_convnext_inf_b200 as acx
+    m = acx.convnext_tiny(drop_path_rate=0.0, after_stem_dim=[252, 56])
+    m.load_state_dict(sd)
+    m = m.to(DEV).eval().set_precision("bf16")
+    assert m._get_engine().frontend == "fused"
+    w = weights.make_waveforms(2, n_samples=L, kind=kind, seed=4)
+    ref = O.frontend(w, sd, torch.float32)
+    ref64 = O.frontend(w, sd, torch.float64)
+    got = m.forward_logmel(w.to(DEV)).cpu()
+    assert got.shape == ref.shape
+    err = (got.double() - ref64).abs()
+    ref_err = (ref.double() - ref64).abs()
+    # bins within 80 dB of the clip maximum (un-normalised dB = before bn0)
+    raw = O.logmel(O.spectrogram(w, sd, torch.float64), sd, torch.float64)
+    mask = raw > raw.amax(dim=(1, 2), keepdim=True) - 80.0
+    print(f"[fused {kind} L={L}] vs fp64: max {err.max():.3e} mean {err.mean():.3e} p99 {err.flatten().quantile(0.99):.3e} "
+          f"masked-max {err[mask].max():.3e} | reference fp32 vs fp64: max {ref_err.max():.3e} mean {ref_err.mean():.3e}")
+    assert torch.isfinite(got).all()
+    assert err.mean() < 5e-4 and err[mask].max() < 5e-3 and err.flatten().quantile(0.99) < 5e-3
