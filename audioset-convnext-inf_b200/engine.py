@@ -153,6 +153,8 @@ class Engine:
             self.frontend, self.mlp = "simt", "gemm"
         self._ws = {}
         self._prof = None
+        self._prof_only = None
+        self.launches = 0
 
     # ---- workspace ------------------------------------------------------------------------------
     def _workspace(self, n, L):
@@ -182,7 +184,8 @@ class Engine:
 
     # ---- per-kernel device timing (tools/time_stages.py, bench.py roofline leg) ------------------------
     def _call(self, tag, name, *args):
-        if self._prof is None:
+        self.launches += 1
+        if self._prof is None or (self._prof_only is not None and not tag.startswith(self._prof_only)):
             N.call(name, *args)
             return
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -194,13 +197,55 @@ class Engine:
     def profile(self, wave, want=("logits",)):
         """Run once with a CUDA-event pair around every kernel launch (serialised on the current
         stream); returns [(tag, milliseconds)] in launch order."""
-        self._prof = []
-        try:
-            self.run(wave, want)
-            torch.cuda.synchronize(self.device)
-            return [(tag, e0.elapsed_time(e1)) for tag, e0, e1 in self._prof]
-        finally:
-            self._prof = None
+        self.start_timing(None)
+        self.run(wave, want)
+        return self.stop_timing()
+
+    def start_timing(self, only=None):
+        """Record a CUDA-event pair around every launch whose tag starts with `only` (all if None)."""
+        self._prof, self._prof_only = [], only
+
+    def stop_timing(self):
+        torch.cuda.synchronize(self.device)
+        res = [(tag, e0.elapsed_time(e1)) for tag, e0, e1 in self._prof]
+        self._prof, self._prof_only = None, None
+        return res
+
+    def algorithmic_work(self, tag, n, L):
+        """Roofline numerator of ONE launch of kernel `tag` on a chunk of n clips:
+        ("tensor", FLOPs) for the GEMM kernels, ("hbm", bytes) for the bandwidth kernels -- each activation
+        tensor counted once per producing / consuming kernel, split-precision passes counted once."""
+        T, hs = out_time_dims(L)
+        es = self.esize
+        if tag.startswith(("pw1_gelu", "pw2_resid", "ds_")):
+            K, Nn = (int(t[1:]) for t in tag.split("_")[-2:])
+            C = {"pw1_gelu": K, "pw2_resid": Nn, "ds": K // 4}[tag.rsplit("_", 2)[0]]
+            s = DIMS.index(C)
+            M = n * (hs[s + 1] * (28 >> s) if tag.startswith("ds_") else hs[s] * (56 >> s))
+            return "tensor", 2.0 * M * Nn * K
+        if tag.startswith("mlp_fused_c"):
+            C = int(tag[len("mlp_fused_c"):])
+            s = DIMS.index(C)
+            return "tensor", 2.0 * (n * hs[s] * (56 >> s)) * C * 4 * C * 2
+        if tag.startswith("dwconv_ln_c"):
+            C = int(tag[len("dwconv_ln_c"):])
+            s = DIMS.index(C)
+            return "hbm", 2.0 * n * hs[s] * (56 >> s) * C * es
+        if tag.startswith("ln_patchify_c"):
+            C = int(tag[len("ln_patchify_c"):])
+            s = DIMS.index(C)
+            return "hbm", 2.0 * n * hs[s] * (56 >> s) * C * es
+        if tag == "frontend_fused":
+            return "tensor", n * T * 2.0 * (N_FFT * 2 * N_BINS + N_BINS * N_MELS)
+        if tag == "dft_simt":
+            return "tensor", n * T * 2.0 * N_FFT * 2 * N_BINS
+        if tag == "stem":
+            return "hbm", n * (T * N_MELS * 4.0 + hs[0] * 56 * DIMS[0] * es)
+        if tag == "wave_prep":
+            return "hbm", n * L * 4.0 + n * (L + N_FFT) * 4.0
+        if tag == "head":
+            return "hbm", n * hs[3] * 7 * DIMS[3] * es + N_CLASSES * DIMS[3] * 4.0
+        return "hbm", 0.0
 
     # ---- stages (each is one libacx call) ----------------------------------------------------------
     def _frontend(self, wave, ws, n, L, st):
