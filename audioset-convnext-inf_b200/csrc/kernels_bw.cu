@@ -123,148 +123,180 @@ __global__ void __launch_bounds__(256) stem_kernel(const float* __restrict__ log
 }
 
 // =============================================================================================
-// depthwise 7x7 + LayerNorm.  Thread = (strip of 7 output pixels along W) x (channel pair).
-// The 49 taps of the thread's two channels live in registers for the whole block lifetime; per
-// input row the thread loads 13 channel-pairs and issues 98 FMAs (7.5 FMA per load).
-// LayerNorm: two-pass; per-pixel partial sums are reduce-scattered inside each 16-lane group
-// (8 shuffles for 7 pixels) and combined across groups through shared memory in a FIXED order.
+// depthwise 7x7 + LayerNorm (reference convnext.py:76-78).
+// Thread = one channel pair x a strip of 7 output pixels along W x R = 4 consecutive output rows.
+//  * the R+6 input rows slide through registers: each row is loaded ONCE (13 channel-pair words, prefetched one
+//    row ahead) and feeds up to 4 output rows -> 3.25 loads + 6.5 unpack ops per 98 FMAs;
+//  * the 49 taps of every channel live in shared memory as fp32 pairs (one conflict-free LDS.64 per 14 FMAs),
+//    which keeps the kernel at ~110 registers instead of 168-195 when the taps sat in registers;
+//  * LayerNorm statistics are fp32; the R*7 per-pixel partial sums are reduce-scattered inside each 16-lane group
+//    (30 shuffles for 28 pixels) and combined across the C/32 groups through shared memory in a FIXED order, so a
+//    clip's result is bit-identical whatever else is in the batch.  The fp32 instantiation uses the two-pass
+//    variance of F.layer_norm; the bf16 one a single pass (sum and sum of squares together).
 // =============================================================================================
-// Per-pixel sums of 7 values over the 16 lanes of a half-warp: reduce-scatter (8 shuffles instead of 28).
-// On return lanes with (lane & 1) == 0 hold the total of pixel p = bits (3,2,1) of the lane in v[0].
-__device__ __forceinline__ void halfwarp_reduce7(float (&v)[8], int lane) {
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const bool up = lane & 8;
-    const float send = up ? v[i] : v[i + 4];
-    const float keep = up ? v[i + 4] : v[i];
-    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-  }
-#pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    const bool up = lane & 4;
-    const float send = up ? v[i] : v[i + 2];
-    const float keep = up ? v[i + 2] : v[i];
-    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-  }
-  {
-    const bool up = lane & 2;
-    const float send = up ? v[0] : v[1];
-    const float keep = up ? v[1] : v[0];
-    v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-  }
-  v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
-}
+constexpr int DW_R = 4;
 
-// Block-level, ORDER-FIXED reduction of the 7 per-pixel values of a strip over all its C/2 threads, so a clip's
-// result is bit-identical whatever else is in the batch (no atomics).  G = C/32 half-warp groups per strip.
-// Returns the totals in tot[0..6].  Uses two __syncthreads (three when G > 6).
-template <int G>
-__device__ __forceinline__ void strip_allreduce7(float (&v)[8], float (&tot)[7], float* part /*[G][8]*/,
-                                                 float* sums /*[8]*/, int lane, int grp, int cp) {
-  halfwarp_reduce7(v, lane);
-  if ((lane & 1) == 0) part[grp * 8 + ((lane >> 1) & 7)] = v[0];
-  __syncthreads();
-  if (G <= 6) {
+// Sum NV (= 32 or 64) per-thread values over the 16 lanes of a half-warp.  On return lane l (0..15) holds in
+// v[0 .. NV/16) the totals of values [ (NV/16) * rev(l) ... ), where rev is given by slot_of_lane below.
+template <int NV>
+__device__ __forceinline__ void halfwarp_reduce_scatter(float (&v)[NV], int lane) {
 #pragma unroll
-    for (int p = 0; p < 7; ++p) {
-      float t = part[p];
+  for (int off = 8, n = NV / 2; off >= 1; off >>= 1, n >>= 1) {
+    const bool up = lane & off;
 #pragma unroll
-      for (int g = 1; g < G; ++g) t += part[g * 8 + p];
-      tot[p] = t;
+    for (int i = 0; i < n; ++i) {
+      const float send = up ? v[i] : v[i + n];
+      const float keep = up ? v[i + n] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
     }
-    __syncthreads();  // part[] may be rewritten by the next reduction
-  } else {
-    if (cp < 7) {
-      float t = part[cp];
-#pragma unroll
-      for (int g = 1; g < G; ++g) t += part[g * 8 + cp];
-      sums[cp] = t;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int p = 0; p < 7; ++p) tot[p] = sums[p];
-    __syncthreads();
   }
 }
+// first value index owned by `lane` after halfwarp_reduce_scatter<NV>: bit 3 selects the upper half, bit 2 the
+// upper quarter, ...
+template <int NV>
+__device__ __forceinline__ int slot_of_lane(int lane) {
+  return ((lane & 8) ? NV / 2 : 0) + ((lane & 4) ? NV / 4 : 0) + ((lane & 2) ? NV / 8 : 0) + ((lane & 1) ? NV / 16 : 0);
+}
 
-template <typename T, int C, int S, int ROWS>
+template <typename T, int C, int S>
 __global__ void __launch_bounds__(S* C / 2)
     dwconv_ln_kernel(const T* __restrict__ x, const T* __restrict__ w, const float* __restrict__ bias,
                      const float* __restrict__ ln_w, const float* __restrict__ ln_b, T* __restrict__ y, int H,
                      int W) {
   using P = Pair<T>;
   using PT = typename P::type;
-  constexpr int TPS = C / 2;  // threads per strip
-  constexpr int G = C / 32;   // half-warp groups per strip
+  constexpr int R = DW_R;
+  constexpr int NP = R * 7;         // 28 pixels per thread
+  constexpr int TPS = C / 2;        // threads per strip
+  constexpr int G = C / 32;         // half-warp groups per strip
+  constexpr bool kTwoPass = sizeof(T) == 4;
+  constexpr int NV = kTwoPass ? 32 : 64;   // values reduced per pass (28 sums [+ 28 sums of squares], padded)
   static_assert((S * TPS) % 32 == 0, "block must be whole warps (full-mask shuffles)");
-  __shared__ float part[S][G][8];
-  __shared__ float sums[S][8];
+  extern __shared__ __align__(16) float dsm[];
+  float2* sw = reinterpret_cast<float2*>(dsm);                 // [49][TPS] taps as fp32 pairs
+  float* part = dsm + 2 * 49 * TPS;                             // [S][G][NV]
+  float* tot = part + S * G * NV;                               // [S][NV]
   const int tid = threadIdx.x;
   const int lane = tid & 31;
   const int cp = tid % TPS;
   const int s = tid / TPS;
   const int grp = cp >> 4;
-  const int strip = blockIdx.x * S + s;
-  const int w0 = strip * 7;
+  const int w0 = (blockIdx.x * S + s) * 7;
   const int b = blockIdx.z;
-  const int h_begin = blockIdx.y * ROWS;
-  const PT* xp = reinterpret_cast<const PT*>(x) + (size_t)b * H * W * TPS;
-  PT* yp = reinterpret_cast<PT*>(y) + (size_t)b * H * W * TPS;
+  const int h0 = blockIdx.y * R;
+  const PT* xp = reinterpret_cast<const PT*>(x) + (size_t)b * H * W * TPS + cp;
+  PT* yp = reinterpret_cast<PT*>(y) + (size_t)b * H * W * TPS + cp;
 
-  PT wr[49];
-#pragma unroll
-  for (int k = 0; k < 49; ++k) wr[k] = reinterpret_cast<const PT*>(w)[k * TPS + cp];
+  for (int i = tid; i < 49 * TPS; i += S * TPS) sw[i] = P::unpack(reinterpret_cast<const PT*>(w)[i]);
   const float2 bs = make_float2(bias[2 * cp], bias[2 * cp + 1]);
-  const float2 gw = make_float2(ln_w[2 * cp], ln_w[2 * cp + 1]);
-  const float2 gb = make_float2(ln_b[2 * cp], ln_b[2 * cp + 1]);
+  __syncthreads();
 
-  for (int r = 0; r < ROWS; ++r) {
-    const int h = h_begin + r;
-    if (h >= H) break;  // block-uniform
-    float2 acc[7];
+  float2 acc[R][7];
 #pragma unroll
-    for (int p = 0; p < 7; ++p) acc[p] = bs;
+  for (int r = 0; r < R; ++r)
 #pragma unroll
-    for (int ky = 0; ky < 7; ++ky) {
-      const int ih = h + ky - 3;
-      if (ih < 0 || ih >= H) continue;  // block-uniform
-      const PT* row = xp + (size_t)ih * W * TPS + cp;
-      float2 in[13];
+    for (int p = 0; p < 7; ++p) acc[r][p] = bs;
+
+  auto load_row = [&](int ih, PT(&dst)[13]) {
+    const bool row_ok = ih >= 0 && ih < H;
+    const PT* row = xp + (size_t)(row_ok ? ih : 0) * W * TPS;
 #pragma unroll
-      for (int j = 0; j < 13; ++j) {
-        const int iw = w0 - 3 + j;
-        in[j] = (iw >= 0 && iw < W) ? P::unpack(__ldg(row + (size_t)iw * TPS)) : make_float2(0.f, 0.f);
-      }
+    for (int j = 0; j < 13; ++j) {
+      const int iw = w0 - 3 + j;
+      dst[j] = (row_ok && iw >= 0 && iw < W) ? __ldg(row + (size_t)iw * TPS) : PT{};
+    }
+  };
+
+  PT nxt[13];
+  load_row(h0 - 3, nxt);
+#pragma unroll 1
+  for (int i = 0; i < R + 6; ++i) {
+    float2 in[13];
+#pragma unroll
+    for (int j = 0; j < 13; ++j) in[j] = P::unpack(nxt[j]);
+    if (i + 1 < R + 6) load_row(h0 - 3 + i + 1, nxt);          // prefetch the next input row
+    const int ih = h0 - 3 + i;
+    if (ih < 0 || ih >= H) continue;                            // zero padding contributes nothing (block-uniform)
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int ky = i - r;
+      if (ky < 0 || ky > 6) continue;                           // block-uniform
+      const float2* wk = sw + ky * 7 * TPS + cp;
 #pragma unroll
       for (int kx = 0; kx < 7; ++kx) {
-        const float2 wv = P::unpack(wr[ky * 7 + kx]);
+        const float2 wv = wk[kx * TPS];
 #pragma unroll
         for (int p = 0; p < 7; ++p) {
-          acc[p].x = fmaf(in[p + kx].x, wv.x, acc[p].x);
-          acc[p].y = fmaf(in[p + kx].y, wv.y, acc[p].y);
+          acc[r][p].x = fmaf(in[p + kx].x, wv.x, acc[r][p].x);
+          acc[r][p].y = fmaf(in[p + kx].y, wv.y, acc[r][p].y);
         }
       }
     }
-    // ---- LayerNorm over C (two-pass, fp32, fixed summation order) ----------------------------
-    float v[8], tot[7];
+  }
+
+  // ---- LayerNorm over C -------------------------------------------------------------------------------
+  float* my_part = part + (s * G + grp) * NV;
+  float* my_tot = tot + s * NV;
+  constexpr int PER_LANE = NV / 16;
+  auto block_allreduce = [&](float(&v)[NV]) {
+    halfwarp_reduce_scatter<NV>(v, lane);
+    const int slot = slot_of_lane<NV>(lane & 15);
 #pragma unroll
-    for (int p = 0; p < 7; ++p) v[p] = acc[p].x + acc[p].y;
-    v[7] = 0.f;
-    strip_allreduce7<G>(v, tot, &part[s][0][0], &sums[s][0], lane, grp, cp);
+    for (int q = 0; q < PER_LANE; ++q) my_part[slot + q] = v[q];
+    __syncthreads();
+    for (int q = cp; q < NV; q += TPS) {                        // fixed-order sum over the G groups
+      float t = part[(s * G) * NV + q];
 #pragma unroll
-    for (int p = 0; p < 7; ++p) {
-      const float mean = tot[p] * (1.0f / C);
-      acc[p].x -= mean;
-      acc[p].y -= mean;
-      v[p] = acc[p].x * acc[p].x + acc[p].y * acc[p].y;
+      for (int g = 1; g < G; ++g) t += part[(s * G + g) * NV + q];
+      my_tot[q] = t;
     }
-    v[7] = 0.f;
-    strip_allreduce7<G>(v, tot, &part[s][0][0], &sums[s][0], lane, grp, cp);
-    PT* orow = yp + ((size_t)h * W + w0) * TPS + cp;
+    __syncthreads();
+  };
+  float mean[NP], rstd[NP];
+  if (kTwoPass) {
+    float v[NV];
+#pragma unroll
+    for (int q = 0; q < NV; ++q) v[q] = q < NP ? acc[q / 7][q % 7].x + acc[q / 7][q % 7].y : 0.f;
+    block_allreduce(v);
+#pragma unroll
+    for (int q = 0; q < NP; ++q) {
+      mean[q] = my_tot[q] * (1.0f / C);
+      const float dx = acc[q / 7][q % 7].x - mean[q], dy = acc[q / 7][q % 7].y - mean[q];
+      v[q] = dx * dx + dy * dy;
+    }
+#pragma unroll
+    for (int q = NP; q < NV; ++q) v[q] = 0.f;
+    block_allreduce(v);   // the first barrier inside also orders the my_tot reads above before its rewrite
+#pragma unroll
+    for (int q = 0; q < NP; ++q) rstd[q] = rsqrtf(my_tot[q] * (1.0f / C) + 1e-6f);
+  } else {
+    float v[NV];
+#pragma unroll
+    for (int q = 0; q < 32; ++q) {
+      const float ax = q < NP ? acc[q / 7][q % 7].x : 0.f, ay = q < NP ? acc[q / 7][q % 7].y : 0.f;
+      v[q] = ax + ay;
+      v[32 + q] = ax * ax + ay * ay;
+    }
+    block_allreduce(v);
+#pragma unroll
+    for (int q = 0; q < NP; ++q) {
+      mean[q] = my_tot[q] * (1.0f / C);
+      const float var = fmaxf(my_tot[32 + q] * (1.0f / C) - mean[q] * mean[q], 0.f);
+      rstd[q] = rsqrtf(var + 1e-6f);
+    }
+  }
+  const float2 gw = make_float2(ln_w[2 * cp], ln_w[2 * cp + 1]);
+  const float2 gb = make_float2(ln_b[2 * cp], ln_b[2 * cp + 1]);
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int h = h0 + r;
+    if (h >= H) break;
+    PT* orow = yp + ((size_t)h * W + w0) * TPS;
 #pragma unroll
     for (int p = 0; p < 7; ++p) {
-      const float rstd = rsqrtf(tot[p] * (1.0f / C) + 1e-6f);
-      orow[(size_t)p * TPS] = P::pack(acc[p].x * rstd * gw.x + gb.x, acc[p].y * rstd * gw.y + gb.y);
+      const int q = r * 7 + p;
+      const float sc = rstd[q];
+      orow[(size_t)p * TPS] = P::pack((acc[r][p].x - mean[q]) * sc * gw.x + gb.x, (acc[r][p].y - mean[q]) * sc * gw.y + gb.y);
     }
   }
 }
@@ -439,14 +471,22 @@ __global__ void nhwc_to_nchw_kernel(const T* __restrict__ x, float* __restrict__
 }
 
 // ---- launch helpers ---------------------------------------------------------------------------
-template <typename T, int C, int S, int ROWS>
+template <typename T, int C, int S>
 static int launch_dwconv(const void* x, const void* w, const float* bias, const float* ln_w, const float* ln_b,
                          void* y, int B, int H, int W, cudaStream_t st) {
   const int strips = W / 7;
   ACX_CHECK(strips % S == 0, ACX_ERR_ARG, "dwconv_ln: W/7=%d not a multiple of strips-per-block %d", strips, S);
-  dim3 grid(strips / S, ceil_div(H, ROWS), B);
-  dwconv_ln_kernel<T, C, S, ROWS><<<grid, S * C / 2, 0, st>>>(
-      reinterpret_cast<const T*>(x), reinterpret_cast<const T*>(w), bias, ln_w, ln_b, reinterpret_cast<T*>(y), H, W);
+  constexpr int NV = sizeof(T) == 4 ? 32 : 64;
+  constexpr int SMEM = (2 * 49 * (C / 2) + S * (C / 32) * NV + S * NV) * (int)sizeof(float);
+  auto kern = dwconv_ln_kernel<T, C, S>;
+  static bool configured = false;
+  if (!configured) {
+    ACX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    configured = true;
+  }
+  dim3 grid(strips / S, ceil_div(H, DW_R), B);
+  kern<<<grid, S * C / 2, SMEM, st>>>(reinterpret_cast<const T*>(x), reinterpret_cast<const T*>(w), bias, ln_w, ln_b,
+                                      reinterpret_cast<T*>(y), H, W);
   ACX_CUDA(cudaGetLastError());
   return ACX_OK;
 }
@@ -457,17 +497,17 @@ static int dispatch_dwconv(const void* x, const void* w, const float* bias, cons
   const int strips = W / 7;
   switch (C) {
     case 96:
-      if (strips % 4 == 0) return launch_dwconv<T, 96, 4, 4>(x, w, bias, ln_w, ln_b, y, B, H, W, st);
-      if (strips % 2 == 0) return launch_dwconv<T, 96, 2, 4>(x, w, bias, ln_w, ln_b, y, B, H, W, st);
+      if (strips % 4 == 0) return launch_dwconv<T, 96, 4>(x, w, bias, ln_w, ln_b, y, B, H, W, st);
+      if (strips % 2 == 0) return launch_dwconv<T, 96, 2>(x, w, bias, ln_w, ln_b, y, B, H, W, st);
       set_error("dwconv_ln: C=96 needs an even number of 7-pixel strips per row (W=%d)", W);
       return ACX_ERR_UNSUPPORTED;
     case 192:
-      if (strips % 2 == 0) return launch_dwconv<T, 192, 2, 4>(x, w, bias, ln_w, ln_b, y, B, H, W, st);
-      return launch_dwconv<T, 192, 1, 4>(x, w, bias, ln_w, ln_b, y, B, H, W, st);
+      if (strips % 2 == 0) return launch_dwconv<T, 192, 2>(x, w, bias, ln_w, ln_b, y, B, H, W, st);
+      return launch_dwconv<T, 192, 1>(x, w, bias, ln_w, ln_b, y, B, H, W, st);
     case 384:
-      return launch_dwconv<T, 384, 1, 4>(x, w, bias, ln_w, ln_b, y, B, H, W, st);
+      return launch_dwconv<T, 384, 1>(x, w, bias, ln_w, ln_b, y, B, H, W, st);
     case 768:
-      return launch_dwconv<T, 768, 1, 4>(x, w, bias, ln_w, ln_b, y, B, H, W, st);
+      return launch_dwconv<T, 768, 1>(x, w, bias, ln_w, ln_b, y, B, H, W, st);
     default:
       set_error("dwconv_ln: unsupported channel count %d (ConvNeXt-Tiny dims are 96/192/384/768)", C);
       return ACX_ERR_UNSUPPORTED;
