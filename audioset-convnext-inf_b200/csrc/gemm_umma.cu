@@ -44,38 +44,35 @@ struct GemmCfg {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES_RAW = (196 * 1024) / STAGE_BYTES;
-  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  static constexpr int STAGES_RAW = (176 * 1024) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 6 ? 6 : STAGES_RAW;
   static constexpr int ACC_STRIDE = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
   static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
-  static constexpr int NGROUPS = NEPI / 4;             // column groups sharing a TMEM lane quadrant
-  static constexpr int COLS_PER_GROUP = BN / NGROUPS;
-  static constexpr int CHUNK = (COLS_PER_GROUP % 32 == 0) ? 32 : 16;
+  // epilogue: 8 warps = 4 TMEM lane quadrants x 2 column groups; columns are handed out in chunks of 32
+  static constexpr int CHUNK = 32;
+  static constexpr int NCHUNKS = BN / CHUNK;
+  static constexpr int CH_G0 = (NCHUNKS + 1) / 2;      // chunks of column group 0 (group 1 gets the rest)
   static constexpr int THREADS = 128 + 32 * NEPI;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
-  static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N constraint for M=128");
-  static_assert(COLS_PER_GROUP % CHUNK == 0, "epilogue column split");
+  // per epilogue warp: 2 output staging tiles + 1 residual tile, each 32 rows x 64 B (SWIZZLE_64B)
+  static constexpr int STG_TILE = 32 * CHUNK * 2;
+  static constexpr int STG_PER_WARP = 3 * STG_TILE;
+  static constexpr int OFF_STG = STAGES * STAGE_BYTES;
+  static constexpr int OFF_BAR = OFF_STG + NEPI * STG_PER_WARP;
+  static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024 /*align*/;
+  static_assert(NEPI == 8, "epilogue layout assumes 8 warps");
+  static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "UMMA N constraint for M=128 / 32-column epilogue chunks");
   static_assert(B_BYTES % 1024 == 0, "stage buffers must stay 1024B aligned for SWIZZLE_128B");
+  static_assert(SMEM_BYTES <= 227 * 1024, "smem budget");
 };
-
-template <int CHUNK>
-__device__ __forceinline__ void tmem_ld_chunk(uint32_t taddr, uint32_t (&r)[CHUNK]);
-template <>
-__device__ __forceinline__ void tmem_ld_chunk<32>(uint32_t taddr, uint32_t (&r)[32]) {
-  ptx::tmem_ld_32x32b_x32(taddr, r);
-}
-template <>
-__device__ __forceinline__ void tmem_ld_chunk<16>(uint32_t taddr, uint32_t (&r)[16]) {
-  ptx::tmem_ld_32x32b_x16(taddr, r);
-}
 
 template <int BN, int EPI, int NEPI>
 __global__ void __launch_bounds__(GemmCfg<BN, NEPI>::THREADS, 1)
-    umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmArgs g) {
+    umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                     const __grid_constant__ CUtensorMap tmOut, GemmArgs g) {
   using Cfg = GemmCfg<BN, NEPI>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
   uint64_t* empty_bar = full_bar + Cfg::STAGES;
   uint64_t* tfull_bar = empty_bar + Cfg::STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
@@ -87,6 +84,7 @@ __global__ void __launch_bounds__(GemmCfg<BN, NEPI>::THREADS, 1)
   if (warp == 0 && ptx::elect_one()) {
     ptx::prefetch_tensormap(&tmA);
     ptx::prefetch_tensormap(&tmB);
+    ptx::prefetch_tensormap(&tmOut);
   }
   if (warp == 1 && ptx::elect_one()) {
     for (int s = 0; s < Cfg::STAGES; ++s) {
@@ -172,47 +170,88 @@ __global__ void __launch_bounds__(GemmCfg<BN, NEPI>::THREADS, 1)
     }
   } else if (warp >= 4) {
     // ================================ epilogue =====================================
+    // Each warp owns 32 accumulator rows (its TMEM lane quadrant) x a set of 32-column chunks.  Per chunk:
+    // tcgen05.ld (issued one chunk ahead) -> bias / GELU / gamma*x + residual -> bf16 -> 64B-swizzled smem tile ->
+    // one TMA store (coalesced, asynchronous, clipped at M).  The residual tile is fetched with coalesced 16-byte
+    // loads (8 rows x 64 B per instruction) one chunk ahead and transposed through smem.
     const int ew = warp - 4;
     const int quad = warp & 3;            // TMEM lane quadrant this warp may access
     const int group = ew >> 2;            // column group
+    const int ch_begin = group == 0 ? 0 : Cfg::CH_G0;
+    const int ch_count = group == 0 ? Cfg::CH_G0 : Cfg::NCHUNKS - Cfg::CH_G0;
+    uint8_t* stg = smem + Cfg::OFF_STG + ew * Cfg::STG_PER_WARP;
+    uint8_t* rbuf = stg + 2 * Cfg::STG_TILE;
+    const int sw = (lane >> 1) & 3;       // SWIZZLE_64B: 16-byte chunk j of row r lives at chunk j ^ ((r >> 1) & 3)
+    const int ld_piece = lane & 3, ld_row = lane >> 2;   // coalesced residual fetch: 4 pieces x 8 rows per instruction
     int it = 0;
+    uint32_t store_parity = 0;            // which staging tile the next chunk uses
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const int m0 = (tile / num_n_tiles) * Cfg::BM;
       const int n0 = (tile % num_n_tiles) * BN;
-      const int row = m0 + quad * 32 + lane;
-      const bool row_ok = row < g.M;
+      const int row0 = m0 + quad * 32;
+      uint4 rq[4];
+      auto fetch_resid = [&](int ci) {
+        if (EPI != ACX_EPI_BIAS_SCALE_RESID) return;
+        const int n = n0 + (ch_begin + ci) * Cfg::CHUNK;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int r = row0 + ld_row + 8 * q;
+          rq[q] = make_uint4(0u, 0u, 0u, 0u);
+          if (r < g.M) rq[q] = *reinterpret_cast<const uint4*>(g.resid + (size_t)r * g.N + n + ld_piece * 8);
+        }
+      };
+      fetch_resid(0);   // overlaps the wait for the accumulator
       ptx::mbar_wait(&tfull_bar[acc], acc_phase);
       ptx::tc_fence_after();
-      const uint32_t t_base = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * Cfg::ACC_STRIDE;
-#pragma unroll 1
-      for (int c0 = group * Cfg::COLS_PER_GROUP; c0 < (group + 1) * Cfg::COLS_PER_GROUP; c0 += Cfg::CHUNK) {
-        uint32_t r[Cfg::CHUNK];
-        tmem_ld_chunk<Cfg::CHUNK>(t_base + c0, r);
-        ptx::tmem_ld_wait();
-        const int n = n0 + c0;
-        float v[Cfg::CHUNK];
+      const uint32_t t_base = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * Cfg::ACC_STRIDE +
+                              ch_begin * Cfg::CHUNK;
+      uint32_t ra[32], rb[32];
+      ptx::tmem_ld_32x32b_x32(t_base, ra);
 #pragma unroll
-        for (int j = 0; j < Cfg::CHUNK; j += 4) {
-          const float4 b4 = __ldg(reinterpret_cast<const float4*>(g.bias + n + j));
-          v[j + 0] = __uint_as_float(r[j + 0]) + b4.x;
-          v[j + 1] = __uint_as_float(r[j + 1]) + b4.y;
-          v[j + 2] = __uint_as_float(r[j + 2]) + b4.z;
-          v[j + 3] = __uint_as_float(r[j + 3]) + b4.w;
-        }
-        if (EPI == ACX_EPI_BIAS_GELU) {
+      for (int ci = 0; ci < Cfg::CH_G0; ++ci) {
+        if (ci < ch_count) {
+          uint32_t(&r)[32] = (ci & 1) ? rb : ra;
+          ptx::tmem_ld_wait();
+          if (ci + 1 < ch_count) {
+            ptx::tmem_ld_32x32b_x32(t_base + (ci + 1) * Cfg::CHUNK, (ci & 1) ? ra : rb);
+          } else {
+            // last TMEM read of this accumulator has landed: hand it back to the MMA warp
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
+          }
+          const int n = n0 + (ch_begin + ci) * Cfg::CHUNK;
+          float v[32];
 #pragma unroll
-          for (int j = 0; j < Cfg::CHUNK; ++j) v[j] = gelu_fast(v[j]);
-        }
-        if (EPI == ACX_EPI_BIAS_SCALE_RESID) {
-          if (row_ok) {
-            const uint4* rp = reinterpret_cast<const uint4*>(g.resid + (size_t)row * g.N + n);
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(g.bias + n + j));
+            v[j + 0] = __uint_as_float(r[j + 0]) + b4.x;
+            v[j + 1] = __uint_as_float(r[j + 1]) + b4.y;
+            v[j + 2] = __uint_as_float(r[j + 2]) + b4.z;
+            v[j + 3] = __uint_as_float(r[j + 3]) + b4.w;
+          }
+          if (EPI == ACX_EPI_BIAS_GELU) {
 #pragma unroll
-            for (int j = 0; j < Cfg::CHUNK; j += 8) {
-              const uint4 q = rp[j / 8];  // plain load: `out` may alias `resid` (in-place residual update)
-              const float4 g0 = __ldg(reinterpret_cast<const float4*>(g.gamma + n + j));
-              const float4 g1 = __ldg(reinterpret_cast<const float4*>(g.gamma + n + j + 4));
+            for (int j = 0; j < 32; ++j) v[j] = gelu_fast(v[j]);
+          }
+          if (EPI == ACX_EPI_BIAS_SCALE_RESID) {
+            // transpose the coalesced residual fetch through smem: lane <- its own row
+            __syncwarp();   // previous chunk's reads of rbuf are done
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int rr = ld_row + 8 * q;
+              *reinterpret_cast<uint4*>(rbuf + rr * 64 + ((ld_piece ^ ((rr >> 1) & 3)) << 4)) = rq[q];
+            }
+            __syncwarp();
+            if (ci + 1 < ch_count) fetch_resid(ci + 1);
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+              const uint4 q = *reinterpret_cast<const uint4*>(rbuf + lane * 64 + ((j4 ^ sw) << 4));
+              const float4 g0 = __ldg(reinterpret_cast<const float4*>(g.gamma + n + j4 * 8));
+              const float4 g1 = __ldg(reinterpret_cast<const float4*>(g.gamma + n + j4 * 8 + 4));
+              const int j = j4 * 8;
               float2 f;
               f = Pair<bf16>::unpack(q.x); v[j + 0] = fmaf(g0.x, v[j + 0], f.x); v[j + 1] = fmaf(g0.y, v[j + 1], f.y);
               f = Pair<bf16>::unpack(q.y); v[j + 2] = fmaf(g0.z, v[j + 2], f.x); v[j + 3] = fmaf(g0.w, v[j + 3], f.y);
@@ -220,25 +259,31 @@ __global__ void __launch_bounds__(GemmCfg<BN, NEPI>::THREADS, 1)
               f = Pair<bf16>::unpack(q.w); v[j + 6] = fmaf(g1.z, v[j + 6], f.x); v[j + 7] = fmaf(g1.w, v[j + 7], f.y);
             }
           }
-        }
-        if (row_ok) {
-          uint4* op = reinterpret_cast<uint4*>(g.out + (size_t)row * g.N + n);
+          // staging tile free?  (the TMA store issued two chunks ago has finished reading it)
+          if (lane == 0) ptx::tma_store_wait_read<1>();
+          __syncwarp();
+          uint8_t* tile_smem = stg + store_parity * Cfg::STG_TILE;
 #pragma unroll
-          for (int j = 0; j < Cfg::CHUNK; j += 8) {
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const int j = j4 * 8;
             uint4 q;
             q.x = Pair<bf16>::pack(v[j + 0], v[j + 1]);
             q.y = Pair<bf16>::pack(v[j + 2], v[j + 3]);
             q.z = Pair<bf16>::pack(v[j + 4], v[j + 5]);
             q.w = Pair<bf16>::pack(v[j + 6], v[j + 7]);
-            op[j / 8] = q;
+            *reinterpret_cast<uint4*>(tile_smem + lane * 64 + ((j4 ^ sw) << 4)) = q;
           }
+          ptx::fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            ptx::tma_store_2d(&tmOut, tile_smem, n, row0);
+            ptx::tma_store_commit();
+          }
+          store_parity ^= 1;
         }
       }
-      // all TMEM reads of this accumulator are complete (wait::ld above): hand it back to the MMA warp
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
     }
+    if (lane == 0) ptx::tma_store_wait_read<0>();   // smem must stay valid until the last store has read it
   }
 
   ptx::tc_fence_before();
@@ -250,7 +295,8 @@ __global__ void __launch_bounds__(GemmCfg<BN, NEPI>::THREADS, 1)
 }
 
 template <int BN, int EPI, int NEPI>
-static int launch_umma_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& g, cudaStream_t st) {
+static int launch_umma_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut, const GemmArgs& g,
+                            cudaStream_t st) {
   using Cfg = GemmCfg<BN, NEPI>;
   auto kern = umma_gemm_kernel<BN, EPI, NEPI>;
   static bool configured = false;  // per-instantiation; benign race (idempotent attribute set)
@@ -263,7 +309,7 @@ static int launch_umma_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, cons
   ACX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int tiles = ceil_div(g.M, Cfg::BM) * (g.N / BN);
   const int grid = tiles < sms ? tiles : sms;
-  kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, g);
+  kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, tmOut, g);
   ACX_CUDA(cudaGetLastError());
   return ACX_OK;
 }
@@ -282,11 +328,16 @@ static int dispatch_bn(const CUtensorMap& tmA, const void* W, const GemmArgs& g,
   CUtensorMap tmB;
   int rc = make_tmap_2d_bf16(&tmB, W, (uint64_t)g.K, (uint64_t)g.N, (uint64_t)g.K * 2, 64, (uint32_t)bn);
   if (rc != ACX_OK) return rc;
+  // output: 32-column x 32-row boxes (one per epilogue warp and chunk), 64B swizzle
+  CUtensorMap tmOut;
+  rc = make_tmap_2d_bf16(&tmOut, g.out, (uint64_t)g.N, (uint64_t)g.M, (uint64_t)g.N * 2, 32, 32,
+                         CU_TENSOR_MAP_SWIZZLE_64B);
+  if (rc != ACX_OK) return rc;
   switch (bn) {
-    case 256: return launch_umma_gemm<256, EPI, 8>(tmA, tmB, g, st);
-    case 192: return launch_umma_gemm<192, EPI, 8>(tmA, tmB, g, st);
-    case 128: return launch_umma_gemm<128, EPI, 8>(tmA, tmB, g, st);
-    default:  return launch_umma_gemm<96, EPI, 8>(tmA, tmB, g, st);
+    case 256: return launch_umma_gemm<256, EPI, 8>(tmA, tmB, tmOut, g, st);
+    case 192: return launch_umma_gemm<192, EPI, 8>(tmA, tmB, tmOut, g, st);
+    case 128: return launch_umma_gemm<128, EPI, 8>(tmA, tmB, tmOut, g, st);
+    default:  return launch_umma_gemm<96, EPI, 8>(tmA, tmB, tmOut, g, st);
   }
 }
 

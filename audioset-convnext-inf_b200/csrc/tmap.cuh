@@ -27,12 +27,13 @@ static inline PFN_encodeTiled get_encode_tiled() {
 // Generic rank-R bf16 map, 128B swizzle, OOB reads return zero.
 // dims[0] is the contiguous dimension; strides_bytes[i] is the byte stride of dims[i+1].
 static inline int make_tmap_bf16(CUtensorMap* tm, const void* base, int rank, const cuuint64_t* dims,
-                                 const cuuint64_t* strides_bytes, const cuuint32_t* box) {
+                                 const cuuint64_t* strides_bytes, const cuuint32_t* box,
+                                 CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
   PFN_encodeTiled enc = get_encode_tiled();
   ACX_CHECK(enc != nullptr, ACX_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims,
-                   strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   ACX_CHECK(r == CUDA_SUCCESS, ACX_ERR_CUDA,
             "cuTensorMapEncodeTiled failed (CUresult %d; rank %d dims %llu x %llu, stride %llu B, box %u x %u)", (int)r,
@@ -43,11 +44,12 @@ static inline int make_tmap_bf16(CUtensorMap* tm, const void* base, int rank, co
 
 // Row-major (rows, cols) bf16 matrix, box = box_cols x box_rows.
 static inline int make_tmap_2d_bf16(CUtensorMap* tm, const void* base, uint64_t cols, uint64_t rows,
-                                    uint64_t row_stride_bytes, uint32_t box_cols, uint32_t box_rows) {
+                                    uint64_t row_stride_bytes, uint32_t box_cols, uint32_t box_rows,
+                                    CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
   cuuint64_t dims[2] = {cols, rows};
   cuuint64_t strides[1] = {row_stride_bytes};
   cuuint32_t box[2] = {box_cols, box_rows};
-  return make_tmap_bf16(tm, base, 2, dims, strides, box);
+  return make_tmap_bf16(tm, base, 2, dims, strides, box, swizzle);
 }
 
 }  // namespace acx
