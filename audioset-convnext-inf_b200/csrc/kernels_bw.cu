@@ -66,7 +66,8 @@ __global__ void power_mel_log_kernel(const float* __restrict__ spec, int ld_spec
 
 // =============================================================================================
 // stem: 4x4 stride-4 conv over (T, 224) with 4 rows of zero padding in time, then LayerNorm(96)
-// one warp per output pixel; lane l owns channels l, l+32, l+64.
+// (reference convnext.py:688-691 + :227).  One warp per output pixel, lane l owns channels l, l+32, l+64 and
+// keeps their 48 taps in registers; the 16 patch values are fetched by lanes 0..15 and broadcast by shuffle.
 // =============================================================================================
 template <typename T>
 __global__ void __launch_bounds__(256) stem_kernel(const float* __restrict__ logmel, const float* __restrict__ w,
@@ -74,39 +75,43 @@ __global__ void __launch_bounds__(256) stem_kernel(const float* __restrict__ log
                                                    const float* __restrict__ ln_b, T* __restrict__ out, int B,
                                                    int Tn, int n_mels, int H0, int W0, int pix_per_warp) {
   constexpr int CO = 96;
-  __shared__ float sw[16 * CO];
-  for (int i = threadIdx.x; i < 16 * CO; i += blockDim.x) sw[i] = w[i];
-  __syncthreads();
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const long long total = (long long)B * H0 * W0;
-  long long pix0 = ((long long)blockIdx.x * (blockDim.x >> 5) + warp) * pix_per_warp;
-  float bv[3], gw[3], gb[3];
+  const long long pix0 = ((long long)blockIdx.x * (blockDim.x >> 5) + warp) * pix_per_warp;
+  float wr[16][3], bv[3], gw[3], gb[3];
 #pragma unroll
   for (int j = 0; j < 3; ++j) {
     bv[j] = bias[lane + 32 * j];
     gw[j] = ln_w[lane + 32 * j];
     gb[j] = ln_b[lane + 32 * j];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) wr[k][j] = __ldg(w + k * CO + lane + 32 * j);
   }
-  for (int i = 0; i < pix_per_warp; ++i) {
-    const long long pix = pix0 + i;
-    if (pix >= total) break;
-    const int ox = (int)(pix % W0);
-    const int oy = (int)((pix / W0) % H0);
-    const int b = (int)(pix / ((long long)W0 * H0));
-    // lanes 0..15 fetch the 16 patch values (ky = lane/4, kx = lane%4)
+  auto fetch = [&](long long pix) {
     float v = 0.f;
-    if (lane < 16) {
+    if (lane < 16 && pix < total) {
+      const int ox = (int)(pix % W0);
+      const int oy = (int)((pix / W0) % H0);
+      const int b = (int)(pix / ((long long)W0 * H0));
       const int t = oy * 4 - 4 + (lane >> 2);
       const int m = ox * 4 + (lane & 3);
       if (t >= 0 && t < Tn) v = __ldg(logmel + ((size_t)b * Tn + t) * n_mels + m);
     }
+    return v;
+  };
+  float vnext = fetch(pix0);
+  for (int i = 0; i < pix_per_warp; ++i) {
+    const long long pix = pix0 + i;
+    if (pix >= total) break;
+    const float v = vnext;
+    vnext = fetch(pix + 1 < pix0 + pix_per_warp ? pix + 1 : total);   // prefetch the next patch
     float acc[3] = {bv[0], bv[1], bv[2]};
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
       const float xv = __shfl_sync(0xffffffffu, v, k);
 #pragma unroll
-      for (int j = 0; j < 3; ++j) acc[j] = fmaf(xv, sw[k * CO + lane + 32 * j], acc[j]);
+      for (int j = 0; j < 3; ++j) acc[j] = fmaf(xv, wr[k][j], acc[j]);
     }
     const float mean = warp_sum(acc[0] + acc[1] + acc[2]) * (1.0f / CO);
     float d[3], sq = 0.f;
@@ -125,6 +130,7 @@ __global__ void __launch_bounds__(256) stem_kernel(const float* __restrict__ log
 // =============================================================================================
 // depthwise 7x7 + LayerNorm (reference convnext.py:76-78).
 // Thread = one channel pair x a strip of 7 output pixels along W x R = 4 consecutive output rows.
+//  * the two channels of a pair are processed by ONE packed fp32x2 FMA (FFMA2, new on sm_100);
 //  * the R+6 input rows slide through registers: each row is loaded ONCE (13 channel-pair words, prefetched one
 //    row ahead) and feeds up to 4 output rows -> 3.25 loads + 6.5 unpack ops per 98 FMAs;
 //  * the 49 taps of every channel live in shared memory as fp32 pairs (one conflict-free LDS.64 per 14 FMAs),
@@ -197,38 +203,42 @@ __global__ void __launch_bounds__(S* C / 2)
 #pragma unroll
     for (int p = 0; p < 7; ++p) acc[r][p] = bs;
 
+  // Column halo: only the first / last strip of a row ever leaves the image, so two hoisted predicates replace
+  // the 13 per-element bounds checks; rows outside the image are skipped as a whole (block-uniform).
+  const bool left_ok = w0 > 0, right_ok = w0 + 7 < W;
+  const PT* x0 = xp + ((ptrdiff_t)w0 - 3) * TPS;   // never dereferenced where the predicates are false
   auto load_row = [&](int ih, PT(&dst)[13]) {
     const bool row_ok = ih >= 0 && ih < H;
-    const PT* row = xp + (size_t)(row_ok ? ih : 0) * W * TPS;
+    const PT* row = x0 + (size_t)(row_ok ? ih : 0) * W * TPS;
+    const bool pl = row_ok && left_ok, pr = row_ok && right_ok;
 #pragma unroll
     for (int j = 0; j < 13; ++j) {
-      const int iw = w0 - 3 + j;
-      dst[j] = (row_ok && iw >= 0 && iw < W) ? __ldg(row + (size_t)iw * TPS) : PT{};
+      const bool ok = j < 3 ? pl : (j >= 10 ? pr : row_ok);
+      dst[j] = ok ? __ldg(row + j * TPS) : PT{};
     }
   };
 
   PT nxt[13];
   load_row(h0 - 3, nxt);
-#pragma unroll 1
+  const float2* swc = sw + cp;
+#pragma unroll
   for (int i = 0; i < R + 6; ++i) {
     float2 in[13];
 #pragma unroll
     for (int j = 0; j < 13; ++j) in[j] = P::unpack(nxt[j]);
     if (i + 1 < R + 6) load_row(h0 - 3 + i + 1, nxt);          // prefetch the next input row
     const int ih = h0 - 3 + i;
-    if (ih < 0 || ih >= H) continue;                            // zero padding contributes nothing (block-uniform)
+    if (ih >= 0 && ih < H) {                                    // zero padding contributes nothing (block-uniform)
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-      const int ky = i - r;
-      if (ky < 0 || ky > 6) continue;                           // block-uniform
-      const float2* wk = sw + ky * 7 * TPS + cp;
+      for (int r = 0; r < R; ++r) {
+        const int ky = i - r;                                   // compile-time after unrolling
+        if (ky >= 0 && ky <= 6) {
 #pragma unroll
-      for (int kx = 0; kx < 7; ++kx) {
-        const float2 wv = wk[kx * TPS];
+          for (int kx = 0; kx < 7; ++kx) {
+            const float2 wv = swc[(ky * 7 + kx) * TPS];
 #pragma unroll
-        for (int p = 0; p < 7; ++p) {
-          acc[r][p].x = fmaf(in[p + kx].x, wv.x, acc[r][p].x);
-          acc[r][p].y = fmaf(in[p + kx].y, wv.y, acc[r][p].y);
+            for (int p = 0; p < 7; ++p) acc[r][p] = __ffma2_rn(in[p + kx], wv, acc[r][p]);   // packed fp32x2 FMA (sm_100)
+          }
         }
       }
     }
@@ -302,61 +312,119 @@ __global__ void __launch_bounds__(S* C / 2)
 }
 
 // =============================================================================================
-// channels_first LayerNorm + 2x2 patch gather: one warp per INPUT pixel.
+// channels_first LayerNorm + 2x2 patch gather (reference convnext.py:231-234): 16 lanes per INPUT pixel, each lane
+// holds C/32 channel pairs; a half-warp works on NPIX pixels at once so their loads overlap.
 // =============================================================================================
-template <typename T>
+template <typename T, int C>
 __global__ void __launch_bounds__(256)
     ln_patchify_kernel(const T* __restrict__ x, const float* __restrict__ ln_w, const float* __restrict__ ln_b,
-                       T* __restrict__ a, int B, int H, int W, int C) {
+                       T* __restrict__ a, int B, int H, int W) {
   using P = Pair<T>;
   using PT = typename P::type;
-  constexpr int MAXP = 6;  // C <= 384
-  const int lane = threadIdx.x & 31;
+  constexpr int HALF = C / 2;       // pairs per pixel
+  constexpr int PPL = HALF / 16;    // pairs per lane
+  constexpr int NPIX = 4;           // pixels in flight per half-warp
+  const int l16 = threadIdx.x & 15;
   const int Ho = H / 2, Wo = W / 2;
-  const int half = C / 2;
   const long long total = (long long)B * Ho * 2 * Wo * 2;
-  const long long pix = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (pix >= total) return;
-  const int wi = (int)(pix % (Wo * 2));
-  const int hi = (int)((pix / (Wo * 2)) % (Ho * 2));
-  const int b = (int)(pix / ((long long)Wo * 2 * Ho * 2));
-  const PT* src = reinterpret_cast<const PT*>(x) + (((size_t)b * H + hi) * W + wi) * half;
-  float2 v[MAXP];
-  float sum = 0.f;
+  const long long hw = (long long)blockIdx.x * (blockDim.x >> 4) + (threadIdx.x >> 4);
+  float2 g[PPL], be[PPL];
 #pragma unroll
-  for (int j = 0; j < MAXP; ++j) {
-    const int cp = lane + 32 * j;
-    v[j] = (cp < half) ? P::unpack(__ldg(src + cp)) : make_float2(0.f, 0.f);
-    sum += v[j].x + v[j].y;
+  for (int j = 0; j < PPL; ++j) {
+    g[j] = *reinterpret_cast<const float2*>(ln_w + 2 * (l16 + 16 * j));
+    be[j] = *reinterpret_cast<const float2*>(ln_b + 2 * (l16 + 16 * j));
   }
-  const float mean = warp_sum(sum) / C;
-  float sq = 0.f;
+  float2 v[NPIX][PPL];
+  size_t dst_off[NPIX];
+  bool ok[NPIX];
 #pragma unroll
-  for (int j = 0; j < MAXP; ++j) {
-    const int cp = lane + 32 * j;
-    if (cp < half) {
-      v[j].x -= mean;
-      v[j].y -= mean;
-      sq += v[j].x * v[j].x + v[j].y * v[j].y;
+  for (int q = 0; q < NPIX; ++q) {
+    const long long pix = hw * NPIX + q;
+    ok[q] = pix < total;
+    const long long pp = ok[q] ? pix : 0;
+    const int wi = (int)(pp % (Wo * 2));
+    const int hi = (int)((pp / (Wo * 2)) % (Ho * 2));
+    const int b = (int)(pp / ((long long)Wo * 2 * Ho * 2));
+    const PT* src = reinterpret_cast<const PT*>(x) + (((size_t)b * H + hi) * W + wi) * HALF;
+    const size_t m = ((size_t)b * Ho + (hi >> 1)) * Wo + (wi >> 1);
+    dst_off[q] = m * (size_t)(4 * HALF) + (size_t)((hi & 1) * 2 + (wi & 1)) * HALF;
+#pragma unroll
+    for (int j = 0; j < PPL; ++j) v[q][j] = P::unpack(__ldg(src + l16 + 16 * j));
+  }
+#pragma unroll
+  for (int q = 0; q < NPIX; ++q) {
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < PPL; ++j) sum += v[q][j].x + v[q][j].y;
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum / C;
+    float sq = 0.f;
+#pragma unroll
+    for (int j = 0; j < PPL; ++j) {
+      v[q][j].x -= mean;
+      v[q][j].y -= mean;
+      sq += v[q][j].x * v[q][j].x + v[q][j].y * v[q][j].y;
     }
-  }
-  const float rstd = 1.0f / sqrtf(warp_sum(sq) / C + 1e-6f);
-  const size_t m = ((size_t)b * Ho + (hi >> 1)) * Wo + (wi >> 1);
-  PT* dst = reinterpret_cast<PT*>(a) + m * (size_t)(4 * half) + (size_t)((hi & 1) * 2 + (wi & 1)) * half;
 #pragma unroll
-  for (int j = 0; j < MAXP; ++j) {
-    const int cp = lane + 32 * j;
-    if (cp < half) {
-      const float2 g = *reinterpret_cast<const float2*>(ln_w + 2 * cp);
-      const float2 be = *reinterpret_cast<const float2*>(ln_b + 2 * cp);
-      dst[cp] = P::pack(v[j].x * rstd * g.x + be.x, v[j].y * rstd * g.y + be.y);
+    for (int o = 8; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    const float rstd = 1.0f / sqrtf(sq / C + 1e-6f);
+    if (ok[q]) {
+      PT* dst = reinterpret_cast<PT*>(a) + dst_off[q];
+#pragma unroll
+      for (int j = 0; j < PPL; ++j)
+        dst[l16 + 16 * j] = P::pack(v[q][j].x * rstd * g[j].x + be[j].x, v[q][j].y * rstd * g[j].y + be[j].y);
     }
   }
 }
 
 // =============================================================================================
-// head: one block per clip
+// head (reference convnext.py:279-285, 321-325), two kernels:
+//   pool:   grid (C/64, B): mean over mel (W), then max_t + mean_t  -> pooled (B, C) fp32
+//   ln_fc:  grid (B, 8):    LayerNorm(C) (recomputed per block, 768 values) -> scene; 1/8 of the fc rows -> logits,
+//           sigmoid -> probs
 // =============================================================================================
+template <typename T>
+__global__ void __launch_bounds__(256)
+    head_pool_kernel(const T* __restrict__ x, float* __restrict__ pooled, int H, int W, int C) {
+  using P = Pair<T>;
+  using PT = typename P::type;
+  __shared__ float2 smax[8][32], ssum[8][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b = blockIdx.y;
+  const int cp = blockIdx.x * 32 + lane;                 // channel pair
+  const PT* xb = reinterpret_cast<const PT*>(x) + (size_t)b * H * W * (C / 2) + cp;
+  float2 mx = make_float2(-INFINITY, -INFINITY), sm = make_float2(0.f, 0.f);
+  const float inv_w = 1.0f / W;
+  for (int h = warp; h < H; h += 8) {
+    float2 s = make_float2(0.f, 0.f);
+    for (int wv = 0; wv < W; ++wv) {
+      const float2 f = P::unpack(__ldg(xb + ((size_t)h * W + wv) * (C / 2)));
+      s.x += f.x;
+      s.y += f.y;
+    }
+    s.x *= inv_w;                                        // torch.mean(x, dim=3)   CX:279
+    s.y *= inv_w;
+    mx.x = fmaxf(mx.x, s.x);                             // torch.max(x, dim=2)    CX:280
+    mx.y = fmaxf(mx.y, s.y);
+    sm.x += s.x;                                         // torch.mean(x, dim=2)   CX:281
+    sm.y += s.y;
+  }
+  smax[warp][lane] = mx;
+  ssum[warp][lane] = sm;
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int i = 1; i < 8; ++i) {                        // fixed order
+      mx.x = fmaxf(mx.x, smax[i][lane].x);
+      mx.y = fmaxf(mx.y, smax[i][lane].y);
+      sm.x += ssum[i][lane].x;
+      sm.y += ssum[i][lane].y;
+    }
+    *reinterpret_cast<float2*>(pooled + (size_t)b * C + 2 * cp) = make_float2(mx.x + sm.x / H, mx.y + sm.y / H);  // CX:282
+  }
+}
+
 __device__ __forceinline__ float block_sum_256(float v, float* scratch) {
   v = warp_sum(v);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -369,42 +437,20 @@ __device__ __forceinline__ float block_sum_256(float v, float* scratch) {
   return t;
 }
 
-template <typename T>
 __global__ void __launch_bounds__(256)
-    head_kernel(const T* __restrict__ x, const float* __restrict__ ln_w, const float* __restrict__ ln_b,
-                const float* __restrict__ fc_w, const float* __restrict__ fc_b, float* __restrict__ scene,
-                float* __restrict__ logits, float* __restrict__ probs, int H, int W, int C, int n_cls) {
+    head_ln_fc_kernel(const float* __restrict__ pooled, const float* __restrict__ ln_w, const float* __restrict__ ln_b,
+                      const float* __restrict__ fc_w, const float* __restrict__ fc_b, float* __restrict__ scene,
+                      float* __restrict__ logits, float* __restrict__ probs, int C, int n_cls) {
   constexpr int MAXC = 4;  // C <= 1024
   extern __shared__ float sv[];  // C floats
   __shared__ float scratch[8];
   const int b = blockIdx.x;
   const int tid = threadIdx.x;
-  const T* xb = x + (size_t)b * H * W * C;
-  float mx[MAXC], sm[MAXC];
-#pragma unroll
-  for (int j = 0; j < MAXC; ++j) {
-    mx[j] = -INFINITY;
-    sm[j] = 0.f;
-  }
-  const float inv_w = 1.0f / W;
-  for (int h = 0; h < H; ++h) {
-#pragma unroll
-    for (int j = 0; j < MAXC; ++j) {
-      const int c = tid + 256 * j;
-      if (c < C) {
-        float s = 0.f;
-        for (int wv = 0; wv < W; ++wv) s += to_float(xb[((size_t)h * W + wv) * C + c]);
-        s *= inv_w;                       // torch.mean(x, dim=3)      CX:279
-        mx[j] = fmaxf(mx[j], s);          // torch.max(x, dim=2)       CX:280
-        sm[j] += s;                       // torch.mean(x, dim=2)      CX:281
-      }
-    }
-  }
   float val[MAXC], part = 0.f;
 #pragma unroll
   for (int j = 0; j < MAXC; ++j) {
     const int c = tid + 256 * j;
-    val[j] = (c < C) ? mx[j] + sm[j] / H : 0.f;   // x1 + x2   CX:282
+    val[j] = (c < C) ? pooled[(size_t)b * C + c] : 0.f;
     part += val[j];
   }
   const float mean = block_sum_256(part, scratch) / C;
@@ -424,13 +470,15 @@ __global__ void __launch_bounds__(256)
     if (c < C) {
       const float o = val[j] * rstd * ln_w[c] + ln_b[c];
       sv[c] = o;
-      scene[(size_t)b * C + c] = o;
+      if (blockIdx.y == 0) scene[(size_t)b * C + c] = o;
     }
   }
   __syncthreads();
   if (n_cls <= 0) return;
   const int lane = tid & 31, warp = tid >> 5;
-  for (int o = warp; o < n_cls; o += 8) {
+  const int per = (n_cls + gridDim.y - 1) / gridDim.y;
+  const int o_end = min(n_cls, (int)(blockIdx.y + 1) * per);
+  for (int o = blockIdx.y * per + warp; o < o_end; o += 8) {
     const float* wr = fc_w + (size_t)o * C;
     float acc = 0.f;
     for (int k = lane * 4; k < C; k += 128) {
@@ -581,33 +629,40 @@ int acx_dwconv_ln(const void* x, const void* w, const float* bias, const float* 
 int acx_ln_patchify(const void* x, const float* ln_w, const float* ln_b, void* a, int B, int H, int W, int C,
                     int act_dtype, void* stream) {
   ACX_CHECK(x && ln_w && ln_b && a, ACX_ERR_ARG, "ln_patchify: null pointer");
-  ACX_CHECK(C % 2 == 0 && C <= 384 && H >= 2 && W >= 2, ACX_ERR_ARG, "ln_patchify: unsupported shape C=%d H=%d W=%d", C,
-            H, W);
+  ACX_CHECK((C == 96 || C == 192 || C == 384) && H >= 2 && W >= 2, ACX_ERR_ARG,
+            "ln_patchify: unsupported shape C=%d H=%d W=%d (C must be 96, 192 or 384)", C, H, W);
   const long long total = (long long)B * (H / 2) * 2 * (W / 2) * 2;
-  const int blocks = (int)((total + 7) / 8);
+  const int blocks = (int)((total + 63) / 64);            // 16 half-warps x 4 pixels per block
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (act_dtype == ACX_BF16)
-    ln_patchify_kernel<bf16><<<blocks, 256, 0, st>>>(reinterpret_cast<const bf16*>(x), ln_w, ln_b,
-                                                     reinterpret_cast<bf16*>(a), B, H, W, C);
-  else
-    ln_patchify_kernel<float><<<blocks, 256, 0, st>>>(reinterpret_cast<const float*>(x), ln_w, ln_b,
-                                                      reinterpret_cast<float*>(a), B, H, W, C);
+#define ACX_LNP(TT, CC)                                                                                     \
+  ln_patchify_kernel<TT, CC><<<blocks, 256, 0, st>>>(reinterpret_cast<const TT*>(x), ln_w, ln_b,             \
+                                                     reinterpret_cast<TT*>(a), B, H, W)
+  if (act_dtype == ACX_BF16) {
+    if (C == 96) ACX_LNP(bf16, 96); else if (C == 192) ACX_LNP(bf16, 192); else ACX_LNP(bf16, 384);
+  } else {
+    if (C == 96) ACX_LNP(float, 96); else if (C == 192) ACX_LNP(float, 192); else ACX_LNP(float, 384);
+  }
+#undef ACX_LNP
   ACX_CUDA(cudaGetLastError());
   return ACX_OK;
 }
 
-int acx_head(const void* x, const float* ln_w, const float* ln_b, const float* fc_w, const float* fc_b, float* scene,
-             float* logits, float* probs, int B, int H, int W, int C, int n_cls, int act_dtype, void* stream) {
-  ACX_CHECK(x && ln_w && ln_b && scene, ACX_ERR_ARG, "head: null pointer");
+int acx_head(const void* x, const float* ln_w, const float* ln_b, const float* fc_w, const float* fc_b, float* pooled,
+             float* scene, float* logits, float* probs, int B, int H, int W, int C, int n_cls, int act_dtype,
+             void* stream) {
+  ACX_CHECK(x && ln_w && ln_b && scene && pooled, ACX_ERR_ARG, "head: null pointer");
   ACX_CHECK(n_cls == 0 || (fc_w && fc_b && logits && probs), ACX_ERR_ARG, "head: fc pointers required when n_cls>0");
-  ACX_CHECK(C % 4 == 0 && C <= 1024 && B > 0 && H > 0 && W > 0, ACX_ERR_ARG, "head: unsupported shape");
+  ACX_CHECK(C % 64 == 0 && C <= 1024 && B > 0 && B <= 65535 && H > 0 && W > 0, ACX_ERR_ARG, "head: unsupported shape");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  dim3 pgrid(C / 64, B);
   if (act_dtype == ACX_BF16)
-    head_kernel<bf16><<<B, 256, C * sizeof(float), st>>>(reinterpret_cast<const bf16*>(x), ln_w, ln_b, fc_w, fc_b,
-                                                         scene, logits, probs, H, W, C, n_cls);
+    head_pool_kernel<bf16><<<pgrid, 256, 0, st>>>(reinterpret_cast<const bf16*>(x), pooled, H, W, C);
   else
-    head_kernel<float><<<B, 256, C * sizeof(float), st>>>(reinterpret_cast<const float*>(x), ln_w, ln_b, fc_w, fc_b,
-                                                          scene, logits, probs, H, W, C, n_cls);
+    head_pool_kernel<float><<<pgrid, 256, 0, st>>>(reinterpret_cast<const float*>(x), pooled, H, W, C);
+  ACX_CUDA(cudaGetLastError());
+  dim3 fgrid(B, n_cls > 0 ? 8 : 1);
+  head_ln_fc_kernel<<<fgrid, 256, C * sizeof(float), st>>>(pooled, ln_w, ln_b, fc_w, fc_b, scene, logits, probs, C,
+                                                           n_cls);
   ACX_CUDA(cudaGetLastError());
   return ACX_OK;
 }

@@ -178,6 +178,7 @@ class Engine:
         ws["x"] = torch.empty(m0 * DIMS[0], device=dev, dtype=adt)
         ws["y"] = torch.empty(m0 * DIMS[0], device=dev, dtype=adt)
         ws["hid"] = torch.empty(m0 * 4 * DIMS[0], device=dev, dtype=adt)
+        ws["pooled"] = torch.empty(n, DIMS[3], device=dev, dtype=torch.float32)
         self._ws.clear()          # keep one shape resident
         self._ws[key] = ws
         return ws
@@ -334,7 +335,8 @@ class Engine:
                 if need_head:
                     w = self.w
                     self._call("head", "acx_head", x, w.norm_w.data_ptr(), w.norm_b.data_ptr(), w.fc_w.data_ptr(),
-                           w.fc_b.data_ptr(), out["scene"][b0:].data_ptr(), out["logits"][b0:].data_ptr(),
+                           w.fc_b.data_ptr(), ws["pooled"].data_ptr(), out["scene"][b0:].data_ptr(),
+                           out["logits"][b0:].data_ptr(),
                            out["probs"][b0:].data_ptr(), n, hs[3], 7, DIMS[3], N_CLASSES, self.adt, st)
                 if "frame" in want:
                     self._call("frame_nchw", "acx_nhwc_to_nchw_f32", x, out["frame"][b0:].data_ptr(), n, hs[3], 7, DIMS[3], self.adt, st)

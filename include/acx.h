@@ -109,10 +109,11 @@ ACX_API int acx_mlp_fused(const void* y, void* x, const void* w1, const float* b
                   const float* gamma, int M, int C, void* stream);
 
 /* ---- tail: mean over mel, max_t + mean_t, LayerNorm(768), fc 768->527, sigmoid (CX:279-285, 321-325) */
-/* x (B,H,W,C) act_dtype -> scene (B,C) fp32 [post-LN], logits (B,n_cls), probs (B,n_cls). */
+/* x (B,H,W,C) act_dtype -> scene (B,C) fp32 [post-LN], logits (B,n_cls), probs (B,n_cls).
+ * pooled (B,C) fp32 is caller-provided scratch (the pre-LayerNorm pooled vector). */
 ACX_API int acx_head(const void* x, const float* ln_w, const float* ln_b, const float* fc_w, const float* fc_b,
-             float* scene, float* logits, float* probs, int B, int H, int W, int C, int n_cls, int act_dtype,
-             void* stream);
+             float* pooled, float* scene, float* logits, float* probs, int B, int H, int W, int C, int n_cls,
+             int act_dtype, void* stream);
 
 /* x (B,H,W,C) act_dtype -> out (B,C,H,W) fp32: the layout forward_frame_embeddings returns (CX:399-402). */
 ACX_API int acx_nhwc_to_nchw_f32(const void* x, float* out, int B, int H, int W, int C, int act_dtype, void* stream);

@@ -156,8 +156,9 @@ def test_head_and_frame_layout(sd, H, dtype):
     logits = torch.empty(B, 527, device=DEV)
     probs = torch.empty(B, 527, device=DEV)
     t = [sd[k].to(DEV) for k in ("norm.weight", "norm.bias", "head_audioset.weight", "head_audioset.bias")]
+    pooled = torch.empty(B, 768, device=DEV)
     N.call("acx_head", xd.data_ptr(), t[0].data_ptr(), t[1].data_ptr(), t[2].data_ptr(), t[3].data_ptr(),
-           scene.data_ptr(), logits.data_ptr(), probs.data_ptr(), B, H, 7, 768, 527, _adt(dtype), _st())
+           pooled.data_ptr(), scene.data_ptr(), logits.data_ptr(), probs.data_ptr(), B, H, 7, 768, 527, _adt(dtype), _st())
     assert (scene.cpu() - scene_ref).abs().max() < 1e-4
     assert (logits.cpu() - logits_ref).abs().max() < 2e-4
     assert (probs.cpu() - probs_ref).abs().max() < 1e-4
