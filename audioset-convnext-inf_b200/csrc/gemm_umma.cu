@@ -38,6 +38,23 @@ __device__ __forceinline__ float gelu_fast(float x) {
   return fmaf(hx, t, hx);
 }
 
+// Two elements at a time with the packed fp32x2 pipe ops of sm_100 (FMUL2 / FFMA2): the polynomial and the final
+// blend cost one instruction per PAIR; only the clamp and MUFU.TANH stay scalar.
+__device__ __forceinline__ float2 gelu_fast2(float2 x) {
+  float2 x2 = __fmul2_rn(x, x);
+  x2.x = fminf(x2.x, 50.0f);
+  x2.y = fminf(x2.y, 50.0f);
+  const float2 p = __ffma2_rn(x2, make_float2(-3.51516788e-04f, -3.51516788e-04f),
+                              make_float2(3.70056460e-02f, 3.70056460e-02f));
+  const float2 q = __ffma2_rn(x2, p, make_float2(7.97507884e-01f, 7.97507884e-01f));
+  const float2 inner = __fmul2_rn(x, q);
+  float2 t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t.x) : "f"(inner.x));
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t.y) : "f"(inner.y));
+  const float2 hx = __fmul2_rn(x, make_float2(0.5f, 0.5f));
+  return __ffma2_rn(hx, t, hx);
+}
+
 template <int BN_, int NEPI_>
 struct GemmCfg {
   static constexpr int BM = 128, BN = BN_, BK = 64, NEPI = NEPI_;
@@ -234,7 +251,11 @@ __global__ void __launch_bounds__(GemmCfg<BN, NEPI>::THREADS, 1)
           }
           if (EPI == ACX_EPI_BIAS_GELU) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = gelu_fast(v[j]);
+            for (int j = 0; j < 32; j += 2) {
+              const float2 o = gelu_fast2(make_float2(v[j], v[j + 1]));
+              v[j] = o.x;
+              v[j + 1] = o.y;
+            }
           }
           if (EPI == ACX_EPI_BIAS_SCALE_RESID) {
             // transpose the coalesced residual fetch through smem: lane <- its own row

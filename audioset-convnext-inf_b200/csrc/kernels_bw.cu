@@ -66,64 +66,106 @@ __global__ void power_mel_log_kernel(const float* __restrict__ spec, int ld_spec
 
 // =============================================================================================
 // stem: 4x4 stride-4 conv over (T, 224) with 4 rows of zero padding in time, then LayerNorm(96)
-// (reference convnext.py:688-691 + :227).  One warp per output pixel, lane l owns channels l, l+32, l+64 and
-// keeps their 48 taps in registers; the 16 patch values are fetched by lanes 0..15 and broadcast by shuffle.
+// (reference convnext.py:688-691 + :227).  One THREAD per output pixel, all 96 channels in registers:
+//  * the 16 patch values are four coalesced float4 loads (consecutive pixels = consecutive 16 B);
+//  * the (16, 96) taps sit in smem and are read with warp-uniform LDS.128 (broadcast), 1 per 4 channels, and
+//    applied with packed fp32x2 FMAs;
+//  * LayerNorm statistics need no cross-thread traffic at all;
+//  * the warp's 32 x 96 outputs (contiguous in HBM) are transposed through padded smem and stored coalesced.
 // =============================================================================================
 template <typename T>
-__global__ void __launch_bounds__(256) stem_kernel(const float* __restrict__ logmel, const float* __restrict__ w,
+__global__ void __launch_bounds__(128) stem_kernel(const float* __restrict__ logmel, const float* __restrict__ w,
                                                    const float* __restrict__ bias, const float* __restrict__ ln_w,
                                                    const float* __restrict__ ln_b, T* __restrict__ out, int B,
-                                                   int Tn, int n_mels, int H0, int W0, int pix_per_warp) {
+                                                   int Tn, int n_mels, int H0, int W0) {
   constexpr int CO = 96;
-  const int lane = threadIdx.x & 31;
-  const int warp = threadIdx.x >> 5;
-  const long long total = (long long)B * H0 * W0;
-  const long long pix0 = ((long long)blockIdx.x * (blockDim.x >> 5) + warp) * pix_per_warp;
-  float wr[16][3], bv[3], gw[3], gb[3];
-#pragma unroll
-  for (int j = 0; j < 3; ++j) {
-    bv[j] = bias[lane + 32 * j];
-    gw[j] = ln_w[lane + 32 * j];
-    gb[j] = ln_b[lane + 32 * j];
-#pragma unroll
-    for (int k = 0; k < 16; ++k) wr[k][j] = __ldg(w + k * CO + lane + 32 * j);
+  constexpr int ROW_BYTES = CO * (int)sizeof(T);       // 192 (bf16) / 384 (fp32)
+  constexpr int ROW_PITCH = ROW_BYTES + 16;            // +16 B: conflict-free 16-byte row writes
+  extern __shared__ __align__(16) uint8_t ssm[];
+  float* sw = reinterpret_cast<float*>(ssm);           // [16][96] taps, then bias / ln_w / ln_b [3][96]
+  uint8_t* stile = ssm + (16 + 3) * CO * 4 + (threadIdx.x >> 5) * 32 * ROW_PITCH;
+  for (int i = threadIdx.x; i < 16 * CO; i += blockDim.x) sw[i] = w[i];
+  for (int i = threadIdx.x; i < CO; i += blockDim.x) {
+    sw[16 * CO + i] = bias[i];
+    sw[17 * CO + i] = ln_w[i];
+    sw[18 * CO + i] = ln_b[i];
   }
-  auto fetch = [&](long long pix) {
-    float v = 0.f;
-    if (lane < 16 && pix < total) {
-      const int ox = (int)(pix % W0);
-      const int oy = (int)((pix / W0) % H0);
-      const int b = (int)(pix / ((long long)W0 * H0));
-      const int t = oy * 4 - 4 + (lane >> 2);
-      const int m = ox * 4 + (lane & 3);
-      if (t >= 0 && t < Tn) v = __ldg(logmel + ((size_t)b * Tn + t) * n_mels + m);
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const long long total = (long long)B * H0 * W0;
+  const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long warp_pix0 = pix - lane;
+  const bool ok = pix < total;
+  float xin[16];
+  {
+    const long long pp = ok ? pix : 0;
+    const int ox = (int)(pp % W0);
+    const int oy = (int)((pp / W0) % H0);
+    const int b = (int)(pp / ((long long)W0 * H0));
+#pragma unroll
+    for (int ky = 0; ky < 4; ++ky) {
+      const int t = oy * 4 - 4 + ky;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (ok && t >= 0 && t < Tn) v = __ldg(reinterpret_cast<const float4*>(logmel + ((size_t)b * Tn + t) * n_mels + ox * 4));
+      xin[ky * 4 + 0] = v.x;
+      xin[ky * 4 + 1] = v.y;
+      xin[ky * 4 + 2] = v.z;
+      xin[ky * 4 + 3] = v.w;
     }
-    return v;
-  };
-  float vnext = fetch(pix0);
-  for (int i = 0; i < pix_per_warp; ++i) {
-    const long long pix = pix0 + i;
-    if (pix >= total) break;
-    const float v = vnext;
-    vnext = fetch(pix + 1 < pix0 + pix_per_warp ? pix + 1 : total);   // prefetch the next patch
-    float acc[3] = {bv[0], bv[1], bv[2]};
+  }
+  float2 acc[CO / 2];
 #pragma unroll
-    for (int k = 0; k < 16; ++k) {
-      const float xv = __shfl_sync(0xffffffffu, v, k);
+  for (int c = 0; c < CO / 2; c += 2) {
+    const float4 b4 = *reinterpret_cast<const float4*>(sw + 16 * CO + 2 * c);
+    acc[c] = make_float2(b4.x, b4.y);
+    acc[c + 1] = make_float2(b4.z, b4.w);
+  }
 #pragma unroll
-      for (int j = 0; j < 3; ++j) acc[j] = fmaf(xv, wr[k][j], acc[j]);
+  for (int k = 0; k < 16; ++k) {
+    const float2 xv = make_float2(xin[k], xin[k]);
+#pragma unroll
+    for (int c = 0; c < CO / 2; c += 2) {
+      const float4 w4 = *reinterpret_cast<const float4*>(sw + k * CO + 2 * c);   // warp-uniform -> broadcast
+      acc[c] = __ffma2_rn(xv, make_float2(w4.x, w4.y), acc[c]);
+      acc[c + 1] = __ffma2_rn(xv, make_float2(w4.z, w4.w), acc[c + 1]);
     }
-    const float mean = warp_sum(acc[0] + acc[1] + acc[2]) * (1.0f / CO);
-    float d[3], sq = 0.f;
+  }
+  float sum = 0.f;
 #pragma unroll
-    for (int j = 0; j < 3; ++j) {
-      d[j] = acc[j] - mean;
-      sq += d[j] * d[j];
+  for (int c = 0; c < CO / 2; ++c) sum += acc[c].x + acc[c].y;
+  const float mean = sum * (1.0f / CO);
+  float sq = 0.f;
+#pragma unroll
+  for (int c = 0; c < CO / 2; ++c) {
+    acc[c].x -= mean;
+    acc[c].y -= mean;
+    sq = fmaf(acc[c].x, acc[c].x, sq);
+    sq = fmaf(acc[c].y, acc[c].y, sq);
+  }
+  const float rstd = rsqrtf(sq * (1.0f / CO) + 1e-6f);
+  // normalise, convert, and write this pixel's row into the warp tile
+  uint8_t* myrow = stile + lane * ROW_PITCH;
+#pragma unroll
+  for (int c = 0; c < CO / 2; c += 2) {
+    const float4 g4 = *reinterpret_cast<const float4*>(sw + 17 * CO + 2 * c);
+    const float4 h4 = *reinterpret_cast<const float4*>(sw + 18 * CO + 2 * c);
+    const float o0 = acc[c].x * rstd * g4.x + h4.x, o1 = acc[c].y * rstd * g4.y + h4.y;
+    const float o2 = acc[c + 1].x * rstd * g4.z + h4.z, o3 = acc[c + 1].y * rstd * g4.w + h4.w;
+    if (sizeof(T) == 2) {
+      *reinterpret_cast<uint2*>(myrow + c * 4) = make_uint2(Pair<bf16>::pack(o0, o1), Pair<bf16>::pack(o2, o3));
+    } else {
+      *reinterpret_cast<float4*>(myrow + c * 8) = make_float4(o0, o1, o2, o3);
     }
-    const float rstd = rsqrtf(warp_sum(sq) * (1.0f / CO) + 1e-6f);
-#pragma unroll
-    for (int j = 0; j < 3; ++j)
-      out[(size_t)pix * CO + lane + 32 * j] = from_float<T>(d[j] * rstd * gw[j] + gb[j]);
+  }
+  __syncwarp();
+  // coalesced copy-out: the warp's 32 rows are contiguous in global memory
+  const long long n_valid = total - warp_pix0 < 32 ? total - warp_pix0 : 32;
+  uint8_t* gdst = reinterpret_cast<uint8_t*>(out) + (size_t)warp_pix0 * ROW_BYTES;
+  constexpr int PIECES = ROW_BYTES / 16;               // 16-byte pieces per row
+  for (int i = lane; i < (int)n_valid * PIECES; i += 32) {
+    const int r = i / PIECES, pc = i % PIECES;
+    *reinterpret_cast<uint4*>(gdst + (size_t)r * ROW_BYTES + pc * 16) =
+        *reinterpret_cast<const uint4*>(stile + r * ROW_PITCH + pc * 16);
   }
 }
 
@@ -603,15 +645,22 @@ int acx_stem(const float* logmel, const float* w, const float* bias, const float
   ACX_CHECK(n_mels % 4 == 0 && B > 0 && T > 0, ACX_ERR_ARG, "stem: n_mels must be a multiple of 4");
   const int H0 = (T + 4) / 4 + 1, W0 = n_mels / 4;
   const long long total = (long long)B * H0 * W0;
-  const int ppw = 8;
-  const int blocks = (int)((total + 8 * ppw - 1) / (8 * ppw));
+  const int blocks = (int)((total + 127) / 128);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (act_dtype == ACX_BF16)
-    stem_kernel<bf16><<<blocks, 256, 0, st>>>(logmel, w, bias, ln_w, ln_b, reinterpret_cast<bf16*>(out), B, T, n_mels,
-                                              H0, W0, ppw);
-  else
-    stem_kernel<float><<<blocks, 256, 0, st>>>(logmel, w, bias, ln_w, ln_b, reinterpret_cast<float*>(out), B, T,
-                                               n_mels, H0, W0, ppw);
+  if (act_dtype == ACX_BF16) {
+    const int smem = 19 * 96 * 4 + 4 * 32 * (96 * 2 + 16);
+    stem_kernel<bf16><<<blocks, 128, smem, st>>>(logmel, w, bias, ln_w, ln_b, reinterpret_cast<bf16*>(out), B, T,
+                                                 n_mels, H0, W0);
+  } else {
+    const int smem = 19 * 96 * 4 + 4 * 32 * (96 * 4 + 16);
+    static bool configured = false;
+    if (!configured) {
+      ACX_CUDA(cudaFuncSetAttribute(stem_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      configured = true;
+    }
+    stem_kernel<float><<<blocks, 128, smem, st>>>(logmel, w, bias, ln_w, ln_b, reinterpret_cast<float*>(out), B, T,
+                                                  n_mels, H0, W0);
+  }
   ACX_CUDA(cudaGetLastError());
   return ACX_OK;
 }

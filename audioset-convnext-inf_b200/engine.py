@@ -152,6 +152,8 @@ class Engine:
         if precision == "fp32":
             self.frontend, self.mlp = "simt", "gemm"
         self._ws = {}
+        self._graphs = {}
+        self.use_graph = os.environ.get("ACX_GRAPH", "1") == "1" and precision == "bf16"
         self._prof = None
         self._prof_only = None
         self.launches = 0
@@ -179,7 +181,13 @@ class Engine:
         ws["y"] = torch.empty(m0 * DIMS[0], device=dev, dtype=adt)
         ws["hid"] = torch.empty(m0 * 4 * DIMS[0], device=dev, dtype=adt)
         ws["pooled"] = torch.empty(n, DIMS[3], device=dev, dtype=torch.float32)
+        # static outputs so that a captured CUDA graph can be replayed for any caller-owned output tensor
+        ws["scene"] = torch.empty(n, DIMS[3], device=dev, dtype=torch.float32)
+        ws["logits"] = torch.empty(n, N_CLASSES, device=dev, dtype=torch.float32)
+        ws["probs"] = torch.empty(n, N_CLASSES, device=dev, dtype=torch.float32)
+        ws["frame"] = torch.empty(n, DIMS[3], hs[3], 7, device=dev, dtype=torch.float32)
         self._ws.clear()          # keep one shape resident
+        self._graphs.clear()      # captured graphs point into the old workspace
         self._ws[key] = ws
         return ws
 
@@ -249,17 +257,24 @@ class Engine:
         return "hbm", 0.0
 
     # ---- stages (each is one libacx call) ----------------------------------------------------------
-    def _frontend(self, wave, ws, n, L, st):
+    def _wave_prep(self, wave, ws, n, L, st):
+        """Reads the caller's tensor -> stays outside any captured graph."""
+        ld_pad = ws["ld_pad"]
+        if self.frontend == "fused":
+            self._call("wave_prep", "acx_wave_prep", wave.data_ptr(), ws["wav_hi"].data_ptr(), ws["wav_lo"].data_ptr(),
+                       n, L, N_FFT, ld_pad, N.ACX_BF16, st)
+        else:
+            self._call("wave_prep", "acx_wave_prep", wave.data_ptr(), ws["wav_pad"].data_ptr(), 0, n, L, N_FFT, ld_pad,
+                       N.ACX_F32, st)
+
+    def _frontend(self, ws, n, L, st):
         w = self.w
         T, ld_pad = ws["T"], ws["ld_pad"]
         if self.frontend == "fused":
-            self._call("wave_prep", "acx_wave_prep", wave.data_ptr(), ws["wav_hi"].data_ptr(), ws["wav_lo"].data_ptr(), n, L, N_FFT,
-                   ld_pad, N.ACX_BF16, st)
             self._call("frontend_fused", "acx_frontend_fused", ws["wav_hi"].data_ptr(), ws["wav_lo"].data_ptr(), ld_pad,
                    w.dft_hi.data_ptr(), w.dft_lo.data_ptr(), w.melc_hi.data_ptr(), w.melc_lo.data_ptr(), w.n_chunks,
                    w.bn_scale.data_ptr(), w.bn_shift.data_ptr(), ws["logmel"].data_ptr(), n, T, N_FFT, HOP, N_MELS, st)
         else:
-            self._call("wave_prep", "acx_wave_prep", wave.data_ptr(), ws["wav_pad"].data_ptr(), 0, n, L, N_FFT, ld_pad, N.ACX_F32, st)
             self._call("dft_simt", "acx_gemm_f32", ws["wav_pad"].data_ptr(), ld_pad, T, HOP, w.dft_f32.data_ptr(),
                    ws["spec"].data_ptr(), 2 * N_BINS, n * T, 2 * N_BINS, N_FFT, N.EPI_BIAS, 0, 0, 0, st)
             self._call("power_mel_log", "acx_power_mel_log", ws["spec"].data_ptr(), 2 * N_BINS, N_BINS, w.melT.data_ptr(),
@@ -299,6 +314,37 @@ class Engine:
                 Mo = n * ws["hs"][s + 1] * Wd
                 self._gemm(y, d["w"].data_ptr(), x, Mo, 2 * C, 4 * C, N.EPI_BIAS, d["b"].data_ptr(), 0, 0, st)
 
+    def _body(self, ws, n, L, st, trunk, need_head, need_frame):
+        """Everything after wave_prep for one chunk; writes only into the workspace (graph-capturable)."""
+        self._frontend(ws, n, L, st)
+        if not trunk:
+            return
+        self._trunk(ws, n, st)
+        x = ws["x"].data_ptr()
+        h3 = ws["hs"][3]
+        if need_head:
+            w = self.w
+            self._call("head", "acx_head", x, w.norm_w.data_ptr(), w.norm_b.data_ptr(), w.fc_w.data_ptr(),
+                       w.fc_b.data_ptr(), ws["pooled"].data_ptr(), ws["scene"].data_ptr(), ws["logits"].data_ptr(),
+                       ws["probs"].data_ptr(), n, h3, 7, DIMS[3], N_CLASSES, self.adt, st)
+        if need_frame:
+            self._call("frame_nchw", "acx_nhwc_to_nchw_f32", x, ws["frame"].data_ptr(), n, h3, 7, DIMS[3], self.adt, st)
+
+    def _capture(self, ws, n, L, trunk, need_head, need_frame):
+        """Capture the chunk's ~65 launches into one CUDA graph (fixed workspace pointers, tensor maps baked
+        into the kernel parameters); one eager pass first so per-kernel attributes are already set."""
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        before = self.launches
+        self._body(ws, n, L, st, trunk, need_head, need_frame)
+        per_replay = self.launches - before
+        torch.cuda.synchronize(self.device)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            cst = torch.cuda.current_stream(self.device).cuda_stream
+            self._body(ws, n, L, cst, trunk, need_head, need_frame)
+        self.launches = before                     # the eager pass is replaced by the first replay; capture launches nothing
+        return g, per_replay
+
     # ---- public -----------------------------------------------------------------------------------
     def run(self, wave, want=("logits",)):
         """wave: (B, L) float32 CUDA tensor.  want: subset of {"logits", "scene", "frame", "logmel"}.
@@ -325,19 +371,19 @@ class Engine:
             for b0 in range(0, B, self.chunk):
                 n = min(self.chunk, B - b0)
                 ws = self._workspace(min(self.chunk, B), L)
-                self._frontend(wave[b0:b0 + n], ws, n, L, st)
-                if "logmel" in want:
-                    out["logmel"][b0:b0 + n].copy_(ws["logmel"][:n])
-                    if len(want) == 1:
-                        continue
-                self._trunk(ws, n, st)
-                x = ws["x"].data_ptr()
-                if need_head:
-                    w = self.w
-                    self._call("head", "acx_head", x, w.norm_w.data_ptr(), w.norm_b.data_ptr(), w.fc_w.data_ptr(),
-                           w.fc_b.data_ptr(), ws["pooled"].data_ptr(), out["scene"][b0:].data_ptr(),
-                           out["logits"][b0:].data_ptr(),
-                           out["probs"][b0:].data_ptr(), n, hs[3], 7, DIMS[3], N_CLASSES, self.adt, st)
-                if "frame" in want:
-                    self._call("frame_nchw", "acx_nhwc_to_nchw_f32", x, out["frame"][b0:].data_ptr(), n, hs[3], 7, DIMS[3], self.adt, st)
+                self._wave_prep(wave[b0:b0 + n], ws, n, L, st)
+                trunk = need_head or "frame" in want
+                key = (n, L, trunk, need_head, "frame" in want)
+                if self.use_graph and self._prof is None:
+                    g = self._graphs.get(key)
+                    if g is None:
+                        g = self._capture(ws, n, L, *key[2:])
+                        self._graphs[key] = g
+                    g[0].replay()
+                    self.launches += g[1]
+                else:
+                    self._body(ws, n, L, st, *key[2:])
+                for name in ("logmel", "scene", "logits", "probs", "frame"):
+                    if name in out:
+                        out[name][b0:b0 + n].copy_(ws[name][:n])
         return out
