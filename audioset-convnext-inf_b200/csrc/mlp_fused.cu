@@ -1,0 +1,433 @@
+// Fused ConvNeXt MLP (reference convnext.py:79-86):
+//     x[M,C] <- x + gamma * ( GELU( y . W1^T + b1 ) . W2^T + b2 )          W1 (4C, C), W2 (C, 4C), bf16
+// One persistent CTA per SM works on 128-row tiles.  The 4C-wide hidden activation never leaves the SM: it is produced
+// 128 columns at a time in TMEM (GEMM1 accumulator D1, double buffered), passed through bias+GELU by the epilogue
+// warps into a K-major, 128B-swizzled bf16 smem tile (double buffered), and consumed from there as the A operand of
+// GEMM2, whose C-wide accumulator D2 stays in TMEM for the whole tile.  HBM traffic per row is 3 C bf16 (y in,
+// residual in, x out) instead of the 3 C + 8 C of the two-kernel form.
+//
+//   warp 0   weight-stream TMA producer: per chunk h the W1 tiles (128 x 64) then the W2 tiles (C x 64) of chunk h-1,
+//            in exactly the order the MMA warp consumes them (mbarrier ring)
+//   warp 1   MMA issuer (tcgen05.mma cta_group::1 kind::f16): GEMM1(h) is issued BEFORE GEMM2(h-1) so the tensor pipe
+//            runs while the epilogue warps turn D1(h-1) into the hidden tile
+//   warp 2   TMEM allocator            warp 3   y-tile (A operand) TMA producer
+//   warps 4..11   epilogue-1 (TMEM -> +b1 -> GELU -> bf16 -> swizzled smem) per chunk, epilogue-2
+//            (TMEM -> +b2, *gamma, +residual -> bf16 -> TMA store) per tile
+// TMEM columns: D2 at 0 (C <= 192 -> 256 reserved), D1[0] at 256, D1[1] at 384.
+#include "common.cuh"
+#include "ptx.cuh"
+#include "tmap.cuh"
+
+namespace acx {
+
+__device__ __forceinline__ float2 mlp_gelu2(float2 x) {   // see gemm_umma.cu::gelu_fast2
+  float2 x2 = __fmul2_rn(x, x);
+  x2.x = fminf(x2.x, 50.0f);
+  x2.y = fminf(x2.y, 50.0f);
+  const float2 p = __ffma2_rn(x2, make_float2(-3.51516788e-04f, -3.51516788e-04f),
+                              make_float2(3.70056460e-02f, 3.70056460e-02f));
+  const float2 q = __ffma2_rn(x2, p, make_float2(7.97507884e-01f, 7.97507884e-01f));
+  const float2 inner = __fmul2_rn(x, q);
+  float2 t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t.x) : "f"(inner.x));
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t.y) : "f"(inner.y));
+  const float2 hx = __fmul2_rn(x, make_float2(0.5f, 0.5f));
+  return __ffma2_rn(hx, t, hx);
+}
+
+struct MlpArgs {
+  bf16* x;            // residual stream, updated in place
+  const float* b1;
+  const float* b2;
+  const float* gamma;
+  int M;
+};
+
+template <int C_>
+struct MlpCfg {
+  static constexpr int C = C_, HD = 4 * C, BM = 128, NH = 128, BK = 64;
+  static constexpr int NC = HD / NH;                  // hidden chunks per tile
+  static constexpr int KB1 = (C + BK - 1) / BK;       // k-blocks of GEMM1
+  static constexpr int KB2 = NH / BK;                 // k-blocks of GEMM2 per chunk
+  static constexpr int A_TILE = BM * BK * 2;          // 16 KB
+  static constexpr int A_BUFS = C <= 96 ? 2 : 1;
+  static constexpr int W1_TILE = NH * BK * 2;         // 16 KB
+  static constexpr int W2_TILE = C * BK * 2;          // 12 / 24 KB
+  static constexpr int SLOT = W1_TILE > W2_TILE ? W1_TILE : W2_TILE;
+  static constexpr int SLOTS = C <= 96 ? 4 : 3;
+  static constexpr int H_TILE = BM * BK * 2;          // one k-block of the hidden tile
+  static constexpr int OFF_A = 0;
+  static constexpr int OFF_RING = OFF_A + A_BUFS * KB1 * A_TILE;
+  static constexpr int OFF_H = OFF_RING + SLOTS * SLOT;
+  static constexpr int OFF_STG = OFF_H + 2 * KB2 * H_TILE;
+  static constexpr int STG_TILE = 32 * 64;            // 32 rows x 32 bf16, SWIZZLE_64B
+  static constexpr int STG_PER_WARP = 2 * STG_TILE;   // output tile + residual tile
+  static constexpr int OFF_BAR = OFF_STG + 8 * STG_PER_WARP;
+  static constexpr int SMEM_BYTES = OFF_BAR + 512 + 1024;
+  static constexpr int D2_COL = 0, D1_COL = 256, TMEM_COLS = 512;
+  static constexpr int OUT_CHUNKS = C / 32;           // 32-column output chunks: 3 / 6
+  static constexpr int OUT_G0 = (OUT_CHUNKS + 1) / 2;
+  static constexpr int THREADS = 384;
+  static_assert(C % 32 == 0 && C <= 192, "D2 must fit 256 TMEM columns");
+  static_assert(SLOT % 1024 == 0 && W2_TILE % 1024 == 0, "swizzle alignment");
+  static_assert(SMEM_BYTES <= 227 * 1024, "smem budget");
+};
+
+template <int C>
+__global__ void __launch_bounds__(384, 1)
+    mlp_fused_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmW1,
+                     const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmOut, MlpArgs a) {
+  using Cfg = MlpCfg<C>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
+  uint64_t* ring_full = bars;                          // [SLOTS]
+  uint64_t* ring_empty = ring_full + Cfg::SLOTS;       // [SLOTS]
+  uint64_t* a_full = ring_empty + Cfg::SLOTS;          // [A_BUFS]
+  uint64_t* a_empty = a_full + Cfg::A_BUFS;            // [A_BUFS]
+  uint64_t* d1_full = a_empty + Cfg::A_BUFS;           // [2]
+  uint64_t* d1_empty = d1_full + 2;                    // [2]
+  uint64_t* h_full = d1_empty + 2;                     // [2]
+  uint64_t* h_empty = h_full + 2;                      // [2]
+  uint64_t* d2_full = h_empty + 2;                     // [1]
+  uint64_t* d2_empty = d2_full + 1;                    // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d2_empty + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && ptx::elect_one()) {
+    ptx::prefetch_tensormap(&tmY);
+    ptx::prefetch_tensormap(&tmW1);
+    ptx::prefetch_tensormap(&tmW2);
+    ptx::prefetch_tensormap(&tmOut);
+  }
+  if (warp == 1 && ptx::elect_one()) {
+    for (int s = 0; s < Cfg::SLOTS; ++s) {
+      ptx::mbar_init(&ring_full[s], 1);
+      ptx::mbar_init(&ring_empty[s], 1);
+    }
+    for (int s = 0; s < Cfg::A_BUFS; ++s) {
+      ptx::mbar_init(&a_full[s], 1);
+      ptx::mbar_init(&a_empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(&d1_full[s], 1);
+      ptx::mbar_init(&d1_empty[s], 8);
+      ptx::mbar_init(&h_full[s], 8);
+      ptx::mbar_init(&h_empty[s], 1);
+    }
+    ptx::mbar_init(d2_full, 1);
+    ptx::mbar_init(d2_empty, 8);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int num_tiles = (a.M + Cfg::BM - 1) / Cfg::BM;
+
+  if (warp == 3) {
+    // ===================== y-tile producer ==================================================================
+    if (ptx::elect_one()) {
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int buf = it % Cfg::A_BUFS;
+        const uint32_t use = it / Cfg::A_BUFS;
+        ptx::mbar_wait(&a_empty[buf], (use & 1) ^ 1);
+        uint8_t* sa = smem + Cfg::OFF_A + buf * Cfg::KB1 * Cfg::A_TILE;
+        ptx::mbar_arrive_expect_tx(&a_full[buf], Cfg::KB1 * Cfg::A_TILE);
+        for (int kb = 0; kb < Cfg::KB1; ++kb)
+          ptx::tma_load_2d(sa + kb * Cfg::A_TILE, &tmY, &a_full[buf], kb * Cfg::BK, tile * Cfg::BM);
+      }
+    }
+  } else if (warp == 0) {
+    // ===================== weight-stream producer ===========================================================
+    if (ptx::elect_one()) {
+      int slot = 0;
+      uint32_t phase = 0;
+      auto next_slot = [&]() -> uint8_t* {
+        ptx::mbar_wait(&ring_empty[slot], phase ^ 1);
+        return smem + Cfg::OFF_RING + slot * Cfg::SLOT;
+      };
+      auto advance = [&]() {
+        if (++slot == Cfg::SLOTS) {
+          slot = 0;
+          phase ^= 1;
+        }
+      };
+      auto load_w2 = [&](int hh) {
+        for (int kb = 0; kb < Cfg::KB2; ++kb) {
+          uint8_t* dst = next_slot();
+          ptx::mbar_arrive_expect_tx(&ring_full[slot], Cfg::W2_TILE);
+          ptx::tma_load_2d(dst, &tmW2, &ring_full[slot], hh * Cfg::NH + kb * Cfg::BK, 0);
+          advance();
+        }
+      };
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int h = 0; h < Cfg::NC; ++h) {
+          for (int kb = 0; kb < Cfg::KB1; ++kb) {
+            uint8_t* dst = next_slot();
+            ptx::mbar_arrive_expect_tx(&ring_full[slot], Cfg::W1_TILE);
+            ptx::tma_load_2d(dst, &tmW1, &ring_full[slot], kb * Cfg::BK, h * Cfg::NH);
+            advance();
+          }
+          if (h >= 1) load_w2(h - 1);
+        }
+        load_w2(Cfg::NC - 1);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer ========================================================================
+    if (ptx::elect_one()) {
+      constexpr uint32_t idesc1 = ptx::umma_idesc_bf16(Cfg::BM, Cfg::NH);
+      constexpr uint32_t idesc2 = ptx::umma_idesc_bf16(Cfg::BM, C);
+      const uint32_t d2 = tmem_base + Cfg::D2_COL;
+      int slot = 0;
+      uint32_t phase = 0;
+      auto advance = [&]() {
+        if (++slot == Cfg::SLOTS) {
+          slot = 0;
+          phase ^= 1;
+        }
+      };
+      int it = 0;
+      uint32_t gc = 0;                                  // global chunk counter (selects D1 / H buffers and parities)
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int abuf = it % Cfg::A_BUFS;
+        const uint32_t ause = it / Cfg::A_BUFS;
+        const uint32_t sa = ptx::smem_u32(smem + Cfg::OFF_A + abuf * Cfg::KB1 * Cfg::A_TILE);
+        auto gemm2 = [&](int hh, uint32_t gch) {
+          const int hb = gch & 1;
+          ptx::mbar_wait(&h_full[hb], (gch >> 1) & 1);          // hidden tile written by the epilogue warps
+          if (hh == 0) ptx::mbar_wait(d2_empty, (it & 1) ^ 1);  // previous tile's D2 drained
+          ptx::tc_fence_after();
+          const uint32_t sh = ptx::smem_u32(smem + Cfg::OFF_H + hb * Cfg::KB2 * Cfg::H_TILE);
+          for (int kb = 0; kb < Cfg::KB2; ++kb) {
+            ptx::mbar_wait(&ring_full[slot], phase);
+            ptx::tc_fence_after();
+            const uint64_t da = ptx::umma_desc_sw128_kmajor(sh + kb * Cfg::H_TILE);
+            const uint64_t db = ptx::umma_desc_sw128_kmajor(ptx::smem_u32(smem + Cfg::OFF_RING + slot * Cfg::SLOT));
+#pragma unroll
+            for (int k = 0; k < Cfg::BK / 16; ++k)
+              ptx::umma_bf16(d2, da + 2 * k, db + 2 * k, idesc2, (hh | kb | k) != 0 ? 1u : 0u);
+            ptx::umma_commit(&ring_empty[slot]);
+            advance();
+          }
+          ptx::umma_commit(&h_empty[hb]);
+        };
+        ptx::mbar_wait(&a_full[abuf], ause & 1);
+        ptx::tc_fence_after();
+        for (int h = 0; h < Cfg::NC; ++h, ++gc) {
+          const int db1 = gc & 1;
+          ptx::mbar_wait(&d1_empty[db1], ((gc >> 1) & 1) ^ 1);
+          ptx::tc_fence_after();
+          const uint32_t d1 = tmem_base + Cfg::D1_COL + db1 * Cfg::NH;
+          for (int kb = 0; kb < Cfg::KB1; ++kb) {
+            ptx::mbar_wait(&ring_full[slot], phase);
+            ptx::tc_fence_after();
+            const uint64_t da = ptx::umma_desc_sw128_kmajor(sa + kb * Cfg::A_TILE);
+            const uint64_t db = ptx::umma_desc_sw128_kmajor(ptx::smem_u32(smem + Cfg::OFF_RING + slot * Cfg::SLOT));
+#pragma unroll
+            for (int k = 0; k < Cfg::BK / 16; ++k)
+              if (kb * Cfg::BK + k * 16 < C) ptx::umma_bf16(d1, da + 2 * k, db + 2 * k, idesc1, (kb | k) != 0 ? 1u : 0u);
+            ptx::umma_commit(&ring_empty[slot]);
+            advance();
+          }
+          ptx::umma_commit(&d1_full[db1]);
+          if (h == Cfg::NC - 1) ptx::umma_commit(&a_empty[abuf]);   // y tile no longer needed
+          if (h >= 1) gemm2(h - 1, gc - 1);
+        }
+        gemm2(Cfg::NC - 1, gc - 1);
+        ptx::umma_commit(d2_full);
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue warps ====================================================================
+    const int ew = warp - 4;
+    const int quad = warp & 3;
+    const int group = ew >> 2;
+    const int row_in_tile = quad * 32 + lane;
+    const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+    uint8_t* stg = smem + Cfg::OFF_STG + ew * Cfg::STG_PER_WARP;
+    uint8_t* rbuf = stg + Cfg::STG_TILE;
+    const int sw64 = (lane >> 1) & 3;
+    const int ld_piece = lane & 3, ld_row = lane >> 2;
+    int it = 0;
+    uint32_t gc = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      // ---- epilogue-1: hidden chunks ---------------------------------------------------------------------
+      for (int h = 0; h < Cfg::NC; ++h, ++gc) {
+        const int buf = gc & 1;
+        const uint32_t par = (gc >> 1) & 1;
+        ptx::mbar_wait(&d1_full[buf], par);
+        ptx::tc_fence_after();
+        const uint32_t t0 = lane_base + Cfg::D1_COL + buf * Cfg::NH + group * 64;
+        uint32_t ra[32], rb[32];
+        ptx::tmem_ld_32x32b_x32(t0, ra);
+        ptx::tmem_ld_32x32b_x32(t0 + 32, rb);
+        ptx::tmem_ld_wait();
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&d1_empty[buf]);          // D1 buffer free for GEMM1(h+2)
+        const float* bias = a.b1 + h * Cfg::NH + group * 64;
+        uint32_t packed[32];
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          const float2 bA = __ldg(reinterpret_cast<const float2*>(bias + j));
+          const float2 bB = __ldg(reinterpret_cast<const float2*>(bias + 32 + j));
+          const float2 oA = mlp_gelu2(make_float2(__uint_as_float(ra[j]) + bA.x, __uint_as_float(ra[j + 1]) + bA.y));
+          const float2 oB = mlp_gelu2(make_float2(__uint_as_float(rb[j]) + bB.x, __uint_as_float(rb[j + 1]) + bB.y));
+          packed[j / 2] = Pair<bf16>::pack(oA.x, oA.y);
+          packed[16 + j / 2] = Pair<bf16>::pack(oB.x, oB.y);
+        }
+        ptx::mbar_wait(&h_empty[buf], par ^ 1);                   // GEMM2(h-2) finished reading this hidden buffer
+        // this warp group's 64 hidden columns are k-block `group` of the hidden tile: one 128 B swizzled row per lane
+        uint8_t* hrow = smem + Cfg::OFF_H + (buf * Cfg::KB2 + group) * Cfg::H_TILE + row_in_tile * 128;
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          *reinterpret_cast<uint4*>(hrow + ((q ^ (row_in_tile & 7)) << 4)) =
+              make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
+        ptx::fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&h_full[buf]);
+      }
+      // ---- epilogue-2: output tile -----------------------------------------------------------------------
+      const int m0 = tile * Cfg::BM;
+      const int row0 = m0 + quad * 32;
+      const int ch_begin = group == 0 ? 0 : Cfg::OUT_G0;
+      const int ch_count = group == 0 ? Cfg::OUT_G0 : Cfg::OUT_CHUNKS - Cfg::OUT_G0;
+      uint4 rq[4];
+      auto fetch_resid = [&](int ci) {
+        const int n = (ch_begin + ci) * 32;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int r = row0 + ld_row + 8 * q;
+          rq[q] = make_uint4(0u, 0u, 0u, 0u);
+          if (r < a.M) rq[q] = *reinterpret_cast<const uint4*>(a.x + (size_t)r * C + n + ld_piece * 8);
+        }
+      };
+      fetch_resid(0);
+      ptx::mbar_wait(d2_full, it & 1);
+      ptx::tc_fence_after();
+#pragma unroll
+      for (int ci = 0; ci < Cfg::OUT_G0; ++ci) {
+        if (ci < ch_count) {
+          const int n = (ch_begin + ci) * 32;
+          uint32_t r[32];
+          ptx::tmem_ld_32x32b_x32(lane_base + Cfg::D2_COL + n, r);
+          ptx::tmem_ld_wait();
+          if (ci + 1 == ch_count) {
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(d2_empty);
+          }
+          __syncwarp();
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int rr = ld_row + 8 * q;
+            *reinterpret_cast<uint4*>(rbuf + rr * 64 + ((ld_piece ^ ((rr >> 1) & 3)) << 4)) = rq[q];
+          }
+          __syncwarp();
+          if (ci + 1 < ch_count) fetch_resid(ci + 1);
+          if (lane == 0) ptx::tma_store_wait_read<0>();          // staging tile free again
+          __syncwarp();
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const uint4 res = *reinterpret_cast<const uint4*>(rbuf + lane * 64 + ((j4 ^ sw64) << 4));
+            const int j = j4 * 8;
+            const float4 bA = __ldg(reinterpret_cast<const float4*>(a.b2 + n + j));
+            const float4 bB = __ldg(reinterpret_cast<const float4*>(a.b2 + n + j + 4));
+            const float4 gA = __ldg(reinterpret_cast<const float4*>(a.gamma + n + j));
+            const float4 gB = __ldg(reinterpret_cast<const float4*>(a.gamma + n + j + 4));
+            float2 f;
+            uint4 o;
+            f = Pair<bf16>::unpack(res.x);
+            o.x = Pair<bf16>::pack(fmaf(gA.x, __uint_as_float(r[j + 0]) + bA.x, f.x), fmaf(gA.y, __uint_as_float(r[j + 1]) + bA.y, f.y));
+            f = Pair<bf16>::unpack(res.y);
+            o.y = Pair<bf16>::pack(fmaf(gA.z, __uint_as_float(r[j + 2]) + bA.z, f.x), fmaf(gA.w, __uint_as_float(r[j + 3]) + bA.w, f.y));
+            f = Pair<bf16>::unpack(res.z);
+            o.z = Pair<bf16>::pack(fmaf(gB.x, __uint_as_float(r[j + 4]) + bB.x, f.x), fmaf(gB.y, __uint_as_float(r[j + 5]) + bB.y, f.y));
+            f = Pair<bf16>::unpack(res.w);
+            o.w = Pair<bf16>::pack(fmaf(gB.z, __uint_as_float(r[j + 6]) + bB.z, f.x), fmaf(gB.w, __uint_as_float(r[j + 7]) + bB.w, f.y));
+            *reinterpret_cast<uint4*>(stg + lane * 64 + ((j4 ^ sw64) << 4)) = o;
+          }
+          ptx::fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            ptx::tma_store_2d(&tmOut, stg, n, row0);
+            ptx::tma_store_commit();
+          }
+        }
+      }
+    }
+    if (lane == 0) ptx::tma_store_wait_read<0>();
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+template <int C>
+static int launch_mlp(const void* y, void* x, const void* w1, const float* b1, const void* w2, const float* b2,
+                      const float* gamma, int M, cudaStream_t st) {
+  using Cfg = MlpCfg<C>;
+  CUtensorMap tmY, tmW1, tmW2, tmOut;
+  int rc = make_tmap_2d_bf16(&tmY, y, C, (uint64_t)M, (uint64_t)C * 2, 64, 128);
+  if (rc != ACX_OK) return rc;
+  rc = make_tmap_2d_bf16(&tmW1, w1, C, Cfg::HD, (uint64_t)C * 2, 64, Cfg::NH);
+  if (rc != ACX_OK) return rc;
+  rc = make_tmap_2d_bf16(&tmW2, w2, Cfg::HD, C, (uint64_t)Cfg::HD * 2, 64, C);
+  if (rc != ACX_OK) return rc;
+  rc = make_tmap_2d_bf16(&tmOut, x, C, (uint64_t)M, (uint64_t)C * 2, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
+  if (rc != ACX_OK) return rc;
+  auto kern = mlp_fused_kernel<C>;
+  static bool configured = false;
+  if (!configured) {
+    ACX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    configured = true;
+  }
+  int dev = 0, sms = 0;
+  ACX_CUDA(cudaGetDevice(&dev));
+  ACX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int tiles = ceil_div(M, Cfg::BM);
+  MlpArgs a;
+  a.x = reinterpret_cast<bf16*>(x);
+  a.b1 = b1;
+  a.b2 = b2;
+  a.gamma = gamma;
+  a.M = M;
+  kern<<<tiles < sms ? tiles : sms, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(tmY, tmW1, tmW2, tmOut, a);
+  ACX_CUDA(cudaGetLastError());
+  return ACX_OK;
+}
+
+}  // namespace acx
+
+using namespace acx;
+
+extern "C" int acx_mlp_fused(const void* y, void* x, const void* w1, const float* b1, const void* w2, const float* b2,
+                             const float* gamma, int M, int C, void* stream) {
+  ACX_CHECK(y && x && w1 && b1 && w2 && b2 && gamma, ACX_ERR_ARG, "mlp_fused: null pointer");
+  ACX_CHECK(M > 0, ACX_ERR_ARG, "mlp_fused: M must be positive");
+  ACX_CHECK(((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w1) |
+              reinterpret_cast<uintptr_t>(w2)) & 15) == 0,
+            ACX_ERR_ARG, "mlp_fused: y, x, w1 and w2 must be 16-byte aligned");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  switch (C) {
+    case 96: return launch_mlp<96>(y, x, w1, b1, w2, b2, gamma, M, st);
+    case 192: return launch_mlp<192>(y, x, w1, b1, w2, b2, gamma, M, st);
+    default:
+      set_error("mlp_fused: C=%d not supported (the fused kernel covers stages 0-1: C = 96, 192; wider stages exceed "
+                "the 512 TMEM columns and use acx_gemm_bf16 twice)", C);
+      return ACX_ERR_UNSUPPORTED;
+  }
+}

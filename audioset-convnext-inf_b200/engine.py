@@ -148,7 +148,7 @@ class Engine:
         self.chunk = int(chunk or os.environ.get("ACX_CHUNK", 32 if precision == "bf16" else 4))
         # which implementation of the two fusable pieces to run (both are libacx kernels)
         self.frontend = frontend or os.environ.get("ACX_FRONTEND", "fused" if precision == "bf16" else "simt")
-        self.mlp = mlp or os.environ.get("ACX_MLP", "gemm")
+        self.mlp = mlp or os.environ.get("ACX_MLP", "fused")
         if precision == "fp32":
             self.frontend, self.mlp = "simt", "gemm"
         self._ws = {}

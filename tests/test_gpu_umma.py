@@ -87,3 +87,44 @@ def test_umma_rejects_bad_arguments():
     b = torch.zeros(100, device=DEV)
     rc = lib.acx_gemm_bf16(t.data_ptr(), t.data_ptr(), t.data_ptr(), 128, 100, 64, 0, b.data_ptr(), 0, 0, 0)
     assert rc != 0 and "multiple" in N.last_error()
+
+
+@pytest.mark.parametrize("C,M", [(96, 128), (96, 1000), (96, 14112 * 2), (192, 300), (192, 3528 * 2), (96, 128 * 400)])
+def test_mlp_fused_matches_reference_block_mlp(C, M):
+    """acx_mlp_fused (hidden tile kept in TMEM/SMEM) vs fp64 evaluation of CX:79-86 on the same bf16 operands,
+    and vs the two-kernel tcgen05 path (pw1+GELU, pw2+gamma+residual)."""
+    g = torch.Generator().manual_seed(C + M)
+    y = torch.randn(M, C, generator=g).to(torch.bfloat16)
+    x = torch.randn(M, C, generator=g).to(torch.bfloat16)
+    w1 = (torch.randn(4 * C, C, generator=g) / C ** 0.5).to(torch.bfloat16)
+    w2 = (torch.randn(C, 4 * C, generator=g) / (4 * C) ** 0.5).to(torch.bfloat16)
+    b1 = torch.randn(4 * C, generator=g) * 0.1
+    b2 = torch.randn(C, generator=g) * 0.1
+    gamma = torch.rand(C, generator=g) * 0.5 + 0.1
+    yd, xd, w1d, w2d, b1d, b2d, gd = (t.to(DEV) for t in (y, x, w1, w2, b1, b2, gamma))
+    hid = F.gelu(yd.double() @ w1d.double().t() + b1d.double())
+    ref = xd.double() + gd.double() * (hid @ w2d.double().t() + b2d.double())
+    st = torch.cuda.current_stream().cuda_stream
+    # two-kernel path (hidden rounded to bf16 in HBM)
+    hbuf = torch.empty(M, 4 * C, device=DEV, dtype=torch.bfloat16)
+    x2 = xd.clone()
+    N.call("acx_gemm_bf16", yd.data_ptr(), w1d.data_ptr(), hbuf.data_ptr(), M, 4 * C, C, N.EPI_BIAS_GELU, b1d.data_ptr(), 0, 0, st)
+    N.call("acx_gemm_bf16", hbuf.data_ptr(), w2d.data_ptr(), x2.data_ptr(), M, C, 4 * C, N.EPI_BIAS_SCALE_RESID,
+           b2d.data_ptr(), gd.data_ptr(), x2.data_ptr(), st)
+    x1 = xd.clone()
+    N.call("acx_mlp_fused", yd.data_ptr(), x1.data_ptr(), w1d.data_ptr(), b1d.data_ptr(), w2d.data_ptr(), b2d.data_ptr(),
+           gd.data_ptr(), M, C, st)
+    torch.cuda.synchronize()
+    err = (x1.double() - ref).abs().max().item()
+    err2 = (x2.double() - ref).abs().max().item()
+    assert torch.isfinite(x1.float()).all()
+    assert err < 0.03 + 0.01 * ref.abs().max().item(), (err, err2)
+    assert (x1.double() - x2.double()).abs().max().item() < 0.05      # same arithmetic up to bf16 rounding of outputs
+
+
+def test_mlp_fused_rejects_wide_stages():
+    t = torch.zeros(128, 384, device=DEV, dtype=torch.bfloat16)
+    f = torch.zeros(1536, device=DEV)
+    rc = N.load().acx_mlp_fused(t.data_ptr(), t.data_ptr(), t.data_ptr(), f.data_ptr(), t.data_ptr(), f.data_ptr(),
+                                f.data_ptr(), 128, 384, 0)
+    assert rc != 0 and "not supported" in N.last_error()
