@@ -61,7 +61,7 @@ struct GemmCfg {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES_RAW = (176 * 1024) / STAGE_BYTES;
+  static constexpr int STAGES_RAW = (160 * 1024) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 6 ? 6 : STAGES_RAW;
   static constexpr int ACC_STRIDE = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
   static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
@@ -75,7 +75,9 @@ struct GemmCfg {
   static constexpr int STG_PER_WARP = 3 * STG_TILE;
   static constexpr int OFF_STG = STAGES * STAGE_BYTES;
   static constexpr int OFF_BAR = OFF_STG + NEPI * STG_PER_WARP;
-  static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024 /*align*/;
+  static constexpr int OFF_VEC = OFF_BAR + 256;        // bias[N] (+ gamma[N]) staged once per CTA (dynamic size)
+  static constexpr int VEC_BYTES = 16 * 1024;          // bias up to 3072 columns, gamma up to 1024
+  static constexpr int SMEM_BYTES = OFF_VEC + VEC_BYTES + 1024 /*align*/;
   static_assert(NEPI == 8, "epilogue layout assumes 8 warps");
   static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "UMMA N constraint for M=128 / 32-column epilogue chunks");
   static_assert(B_BYTES % 1024 == 0, "stage buffers must stay 1024B aligned for SWIZZLE_128B");
@@ -97,6 +99,14 @@ __global__ void __launch_bounds__(GemmCfg<BN, NEPI>::THREADS, 1)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  // per-column vectors: staged in smem once per (persistent) CTA instead of a just-in-time __ldg per chunk, which
+  // ncu showed as the epilogue's dominant stall (long_scoreboard)
+  float* sbias = reinterpret_cast<float*>(smem + Cfg::OFF_VEC);
+  float* sgamma = sbias + g.N;
+  for (int i = threadIdx.x; i < g.N; i += blockDim.x) {
+    sbias[i] = g.bias[i];
+    if (EPI == ACX_EPI_BIAS_SCALE_RESID) sgamma[i] = g.gamma[i];
+  }
 
   if (warp == 0 && ptx::elect_one()) {
     ptx::prefetch_tensormap(&tmA);
@@ -220,7 +230,7 @@ __global__ void __launch_bounds__(GemmCfg<BN, NEPI>::THREADS, 1)
         }
       };
       fetch_resid(0);   // overlaps the wait for the accumulator
-      ptx::mbar_wait(&tfull_bar[acc], acc_phase);
+      ptx::mbar_wait_backoff(&tfull_bar[acc], acc_phase);
       ptx::tc_fence_after();
       const uint32_t t_base = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * Cfg::ACC_STRIDE +
                               ch_begin * Cfg::CHUNK;
@@ -243,7 +253,7 @@ __global__ void __launch_bounds__(GemmCfg<BN, NEPI>::THREADS, 1)
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(g.bias + n + j));
+            const float4 b4 = *reinterpret_cast<const float4*>(sbias + n + j);
             v[j + 0] = __uint_as_float(r[j + 0]) + b4.x;
             v[j + 1] = __uint_as_float(r[j + 1]) + b4.y;
             v[j + 2] = __uint_as_float(r[j + 2]) + b4.z;
@@ -270,8 +280,8 @@ __global__ void __launch_bounds__(GemmCfg<BN, NEPI>::THREADS, 1)
 #pragma unroll
             for (int j4 = 0; j4 < 4; ++j4) {
               const uint4 q = *reinterpret_cast<const uint4*>(rbuf + lane * 64 + ((j4 ^ sw) << 4));
-              const float4 g0 = __ldg(reinterpret_cast<const float4*>(g.gamma + n + j4 * 8));
-              const float4 g1 = __ldg(reinterpret_cast<const float4*>(g.gamma + n + j4 * 8 + 4));
+              const float4 g0 = *reinterpret_cast<const float4*>(sgamma + n + j4 * 8);
+              const float4 g1 = *reinterpret_cast<const float4*>(sgamma + n + j4 * 8 + 4);
               const int j = j4 * 8;
               float2 f;
               f = Pair<bf16>::unpack(q.x); v[j + 0] = fmaf(g0.x, v[j + 0], f.x); v[j + 1] = fmaf(g0.y, v[j + 1], f.y);
@@ -325,12 +335,15 @@ static int launch_umma_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, cons
     ACX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     configured = true;
   }
+  ACX_CHECK(g.N * (EPI == ACX_EPI_BIAS_SCALE_RESID ? 8 : 4) <= Cfg::VEC_BYTES, ACX_ERR_UNSUPPORTED,
+            "gemm_bf16: N=%d exceeds the per-column vectors staged in shared memory", g.N);
+  const int smem_bytes = Cfg::SMEM_BYTES;
   int dev = 0, sms = 0;
   ACX_CUDA(cudaGetDevice(&dev));
   ACX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int tiles = ceil_div(g.M, Cfg::BM) * (g.N / BN);
   const int grid = tiles < sms ? tiles : sms;
-  kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, tmOut, g);
+  kern<<<grid, Cfg::THREADS, smem_bytes, st>>>(tmA, tmB, tmOut, g);
   ACX_CUDA(cudaGetLastError());
   return ACX_OK;
 }

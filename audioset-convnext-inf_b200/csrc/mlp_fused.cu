@@ -61,9 +61,10 @@ struct MlpCfg {
   static constexpr int OFF_H = OFF_RING + SLOTS * SLOT;
   static constexpr int OFF_STG = OFF_H + 2 * KB2 * H_TILE;
   static constexpr int STG_TILE = 32 * 64;            // 32 rows x 32 bf16, SWIZZLE_64B
-  static constexpr int STG_PER_WARP = 2 * STG_TILE;   // output tile + residual tile
+  static constexpr int STG_PER_WARP = STG_TILE;       // one tile: residual transpose in, output staging out
   static constexpr int OFF_BAR = OFF_STG + 8 * STG_PER_WARP;
-  static constexpr int SMEM_BYTES = OFF_BAR + 512 + 1024;
+  static constexpr int OFF_VEC = OFF_BAR + 512;       // b1[4C], b2[C], gamma[C] staged once per CTA
+  static constexpr int SMEM_BYTES = OFF_VEC + (HD + 2 * C) * 4 + 1024;
   static constexpr int D2_COL = 0, D1_COL = 256, TMEM_COLS = 512;
   static constexpr int OUT_CHUNKS = C / 32;           // 32-column output chunks: 3 / 6
   static constexpr int OUT_G0 = (OUT_CHUNKS + 1) / 2;
@@ -95,6 +96,14 @@ __global__ void __launch_bounds__(384, 1)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  float* sb1 = reinterpret_cast<float*>(smem + Cfg::OFF_VEC);
+  float* sb2 = sb1 + Cfg::HD;
+  float* sgamma = sb2 + C;
+  for (int i = threadIdx.x; i < Cfg::HD; i += blockDim.x) sb1[i] = a.b1[i];
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+    sb2[i] = a.b2[i];
+    sgamma[i] = a.gamma[i];
+  }
 
   if (warp == 0 && ptx::elect_one()) {
     ptx::prefetch_tensormap(&tmY);
@@ -254,7 +263,7 @@ __global__ void __launch_bounds__(384, 1)
     const int row_in_tile = quad * 32 + lane;
     const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
     uint8_t* stg = smem + Cfg::OFF_STG + ew * Cfg::STG_PER_WARP;
-    uint8_t* rbuf = stg + Cfg::STG_TILE;
+    uint8_t* rbuf = stg;                                 // shared with the output staging tile (see below)
     const int sw64 = (lane >> 1) & 3;
     const int ld_piece = lane & 3, ld_row = lane >> 2;
     int it = 0;
@@ -264,7 +273,7 @@ __global__ void __launch_bounds__(384, 1)
       for (int h = 0; h < Cfg::NC; ++h, ++gc) {
         const int buf = gc & 1;
         const uint32_t par = (gc >> 1) & 1;
-        ptx::mbar_wait(&d1_full[buf], par);
+        ptx::mbar_wait_backoff(&d1_full[buf], par);
         ptx::tc_fence_after();
         const uint32_t t0 = lane_base + Cfg::D1_COL + buf * Cfg::NH + group * 64;
         uint32_t ra[32], rb[32];
@@ -274,12 +283,12 @@ __global__ void __launch_bounds__(384, 1)
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&d1_empty[buf]);          // D1 buffer free for GEMM1(h+2)
-        const float* bias = a.b1 + h * Cfg::NH + group * 64;
+        const float* bias = sb1 + h * Cfg::NH + group * 64;
         uint32_t packed[32];
 #pragma unroll
         for (int j = 0; j < 32; j += 2) {
-          const float2 bA = __ldg(reinterpret_cast<const float2*>(bias + j));
-          const float2 bB = __ldg(reinterpret_cast<const float2*>(bias + 32 + j));
+          const float2 bA = *reinterpret_cast<const float2*>(bias + j);
+          const float2 bB = *reinterpret_cast<const float2*>(bias + 32 + j);
           const float2 oA = mlp_gelu2(make_float2(__uint_as_float(ra[j]) + bA.x, __uint_as_float(ra[j + 1]) + bA.y));
           const float2 oB = mlp_gelu2(make_float2(__uint_as_float(rb[j]) + bB.x, __uint_as_float(rb[j + 1]) + bB.y));
           packed[j / 2] = Pair<bf16>::pack(oA.x, oA.y);
@@ -312,7 +321,7 @@ __global__ void __launch_bounds__(384, 1)
         }
       };
       fetch_resid(0);
-      ptx::mbar_wait(d2_full, it & 1);
+      ptx::mbar_wait_backoff(d2_full, it & 1);
       ptx::tc_fence_after();
 #pragma unroll
       for (int ci = 0; ci < Cfg::OUT_G0; ++ci) {
@@ -326,6 +335,8 @@ __global__ void __launch_bounds__(384, 1)
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(d2_empty);
           }
+          // the single staging tile first transposes the coalesced residual fetch (lane <- its own row) ...
+          if (lane == 0) ptx::tma_store_wait_read<0>();          // previous chunk's TMA store has read the tile
           __syncwarp();
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
@@ -333,26 +344,27 @@ __global__ void __launch_bounds__(384, 1)
             *reinterpret_cast<uint4*>(rbuf + rr * 64 + ((ld_piece ^ ((rr >> 1) & 3)) << 4)) = rq[q];
           }
           __syncwarp();
+          uint4 res[4];
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) res[j4] = *reinterpret_cast<const uint4*>(rbuf + lane * 64 + ((j4 ^ sw64) << 4));
+          __syncwarp();                                          // ... and is then overwritten with the outputs
           if (ci + 1 < ch_count) fetch_resid(ci + 1);
-          if (lane == 0) ptx::tma_store_wait_read<0>();          // staging tile free again
-          __syncwarp();
 #pragma unroll
           for (int j4 = 0; j4 < 4; ++j4) {
-            const uint4 res = *reinterpret_cast<const uint4*>(rbuf + lane * 64 + ((j4 ^ sw64) << 4));
             const int j = j4 * 8;
-            const float4 bA = __ldg(reinterpret_cast<const float4*>(a.b2 + n + j));
-            const float4 bB = __ldg(reinterpret_cast<const float4*>(a.b2 + n + j + 4));
-            const float4 gA = __ldg(reinterpret_cast<const float4*>(a.gamma + n + j));
-            const float4 gB = __ldg(reinterpret_cast<const float4*>(a.gamma + n + j + 4));
+            const float4 bA = *reinterpret_cast<const float4*>(sb2 + n + j);
+            const float4 bB = *reinterpret_cast<const float4*>(sb2 + n + j + 4);
+            const float4 gA = *reinterpret_cast<const float4*>(sgamma + n + j);
+            const float4 gB = *reinterpret_cast<const float4*>(sgamma + n + j + 4);
             float2 f;
             uint4 o;
-            f = Pair<bf16>::unpack(res.x);
+            f = Pair<bf16>::unpack(res[j4].x);
             o.x = Pair<bf16>::pack(fmaf(gA.x, __uint_as_float(r[j + 0]) + bA.x, f.x), fmaf(gA.y, __uint_as_float(r[j + 1]) + bA.y, f.y));
-            f = Pair<bf16>::unpack(res.y);
+            f = Pair<bf16>::unpack(res[j4].y);
             o.y = Pair<bf16>::pack(fmaf(gA.z, __uint_as_float(r[j + 2]) + bA.z, f.x), fmaf(gA.w, __uint_as_float(r[j + 3]) + bA.w, f.y));
-            f = Pair<bf16>::unpack(res.z);
+            f = Pair<bf16>::unpack(res[j4].z);
             o.z = Pair<bf16>::pack(fmaf(gB.x, __uint_as_float(r[j + 4]) + bB.x, f.x), fmaf(gB.y, __uint_as_float(r[j + 5]) + bB.y, f.y));
-            f = Pair<bf16>::unpack(res.w);
+            f = Pair<bf16>::unpack(res[j4].w);
             o.w = Pair<bf16>::pack(fmaf(gB.z, __uint_as_float(r[j + 6]) + bB.z, f.x), fmaf(gB.w, __uint_as_float(r[j + 7]) + bB.w, f.y));
             *reinterpret_cast<uint4*>(stg + lane * 64 + ((j4 ^ sw64) << 4)) = o;
           }

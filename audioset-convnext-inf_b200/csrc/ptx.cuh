@@ -62,6 +62,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Same, for waits that are expected to be long (epilogue warps waiting for an accumulator): back off between
+// polls so the spinning warp does not steal issue slots from the warps that are computing on the same scheduler.
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  uint32_t spins = 0;
+  do {
+    __nanosleep(64);
+    if (++spins > (ACX_MBAR_SPIN_LIMIT >> 4)) {
+      printf("acx: mbarrier watchdog (backoff) block=%d thread=%d bar=%u parity=%u\n", (int)blockIdx.x,
+             (int)threadIdx.x, smem_u32(bar), parity);
+      __trap();
+    }
+  } while (!mbar_try_wait(bar, parity));
+}
+
 // generic-proxy smem writes -> visible to the async proxy (TMA / tcgen05.mma reads)
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
