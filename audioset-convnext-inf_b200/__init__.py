@@ -8,5 +8,6 @@ from . import _native  # noqa: F401
 from .convnext import (Block, ConvNeXt, LayerNorm, LogmelFilterBank, Spectrogram, convnext_tiny,  # noqa: F401
                        load_checkpoint)
 from .engine import Engine, PackedWeights, out_time_dims  # noqa: F401
+from .pipeline import HostPipeline  # noqa: F401
 
-__all__ = ["ConvNeXt", "convnext_tiny", "Block", "LayerNorm", "Engine", "load_checkpoint"]
+__all__ = ["ConvNeXt", "convnext_tiny", "Block", "LayerNorm", "Engine", "HostPipeline", "load_checkpoint"]

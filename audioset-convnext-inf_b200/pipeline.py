@@ -1,0 +1,82 @@
+"""Host-to-host batch pipeline: the step right before and after the hot path.
+
+The reference's eval loop (`pytorch_utils.forward`, PU:88-137) does, per batch and serially,
+`move_data_to_device(batch)` -> `model(batch)` -> `.data.cpu().numpy()`.  `HostPipeline` keeps that contract (host
+batches in, host results out, same order) but double-buffers: while the kernels of batch i run on the compute
+stream, batch i+1 is copied host->device on a copy stream and the result of batch i-1 is copied back.  Inputs may be
+fp32 waveforms or the int16 PCM the AudioSet HDF5 files store (`/32767` scaling of utilities.py:226-227 applied on
+the device), which halves the H2D bytes.
+"""
+import torch
+
+
+class HostPipeline:
+    def __init__(self, model, want=("logits",), depth=2):
+        self.model = model
+        self.want = tuple(want)
+        self.depth = depth
+        self.eng = model._get_engine()
+        self.dev = self.eng.device
+        self.copy_stream = torch.cuda.Stream(device=self.dev)
+        self._slots = None
+
+    def _alloc(self, batch):
+        B, L = batch.shape
+        slots = []
+        for _ in range(self.depth):
+            slots.append(dict(
+                raw=torch.empty(B, L, device=self.dev, dtype=batch.dtype),
+                f32=torch.empty(B, L, device=self.dev, dtype=torch.float32) if batch.dtype != torch.float32 else None,
+                h2d=torch.cuda.Event(), done=torch.cuda.Event(), free=torch.cuda.Event(), out=None, host=None))
+        self._slots = slots
+        self._shape = (B, L, batch.dtype)
+
+    def run(self, host_batches):
+        """host_batches: iterable of (B, L) CPU tensors (pinned for true overlap), fp32 or int16.
+        Returns a list (same order) of dicts of CPU tensors for the requested outputs."""
+        if self.model.training:
+            raise RuntimeError("inference only: call model.eval() first")
+        results = []
+        pending = []
+        compute = torch.cuda.current_stream(self.dev)
+        with torch.cuda.device(self.dev):
+            for i, hb in enumerate(host_batches):
+                if self._slots is None or self._shape != (hb.shape[0], hb.shape[1], hb.dtype):
+                    self._drain(pending, results)
+                    self._alloc(hb)
+                s = self._slots[i % self.depth]
+                if len(pending) >= self.depth:          # slot reuse: its previous result must be retired first
+                    self._retire(pending.pop(0), results)
+                with torch.cuda.stream(self.copy_stream):
+                    self.copy_stream.wait_event(s["free"])      # kernels that read this slot's input have finished
+                    s["raw"].copy_(hb, non_blocking=True)
+                    s["h2d"].record(self.copy_stream)
+                compute.wait_event(s["h2d"])
+                x = s["raw"]
+                if s["f32"] is not None:                 # int16 PCM -> float (utilities.py:226-227: x / 32767.)
+                    torch.div(x, 32767.0, out=s["f32"])
+                    x = s["f32"]
+                out = self.eng.run(x, want=self.want)
+                s["free"].record(compute)
+                s["done"].record(compute)
+                with torch.cuda.stream(self.copy_stream):
+                    self.copy_stream.wait_event(s["done"])
+                    if s["host"] is None or any(s["host"][k].shape != v.shape for k, v in out.items()):
+                        s["host"] = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in out.items()}
+                    for k, v in out.items():
+                        s["host"][k].copy_(v, non_blocking=True)
+                    s["out"] = out                       # keep device tensors alive until the D2H finished
+                    s["d2h"] = torch.cuda.Event()
+                    s["d2h"].record(self.copy_stream)
+                pending.append(s)
+            self._drain(pending, results)
+        return results
+
+    def _retire(self, s, results):
+        s["d2h"].synchronize()
+        results.append({k: v.clone() for k, v in s["host"].items()})   # the pinned staging buffer is reused
+        s["out"] = None
+
+    def _drain(self, pending, results):
+        while pending:
+            self._retire(pending.pop(0), results)

@@ -131,3 +131,25 @@ def test_bf16_mode_against_oracle_per_stage(models, parity_sd):
     rel = (fr - ref).abs().max() / ref.std()
     print(f"  stage3: max|d|/std {rel:.3e}")
     assert rel < 0.5
+
+
+def test_host_pipeline_matches_direct_calls(models):
+    """HostPipeline (double-buffered H2D / compute / D2H; fp32 and int16 PCM inputs) == direct forward calls."""
+    m = models["bf16"]
+    L = 32000 * 2
+    batches = [weights.make_waveforms(3, n_samples=L, kind="noise", seed=20 + i).pin_memory() for i in range(5)]
+    pipe = acx.HostPipeline(m, want=("logits", "frame"))
+    res = pipe.run(batches)
+    assert len(res) == 5
+    for hb, r in zip(batches, res):
+        d = m.forward_all(hb.to(DEV))
+        assert torch.equal(r["logits"], d["clipwise_logits"].cpu())
+        assert torch.equal(r["probs"], d["clipwise_output"].cpu())
+        assert torch.equal(r["frame"], d["frame_embeddings"].cpu())
+    # int16 PCM as stored in the AudioSet HDF5 files (data_generator.py:70-74, utilities.py:226-227)
+    pcm = [(b * 32767.0).round().clamp(-32767, 32767).to(torch.int16).pin_memory() for b in batches[:2]]
+    res16 = acx.HostPipeline(m).run(pcm)
+    for p, r in zip(pcm, res16):
+        ref_wave = (p.numpy() / 32767.0).astype("float32")        # utilities.py:226-227, on the host
+        d = m(torch.from_numpy(ref_wave).to(DEV))
+        assert torch.equal(r["logits"], d["clipwise_logits"].cpu())
