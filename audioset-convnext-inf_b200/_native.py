@@ -20,6 +20,7 @@ SIGNATURES = {
     "acx_last_error": [],
     "acx_device_ok": [],
     "acx_wave_prep": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
+    "acx_wave_prep_pcm16": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     "acx_power_mel_log": [_vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp],
     "acx_frontend_fused": [_vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     "acx_stem": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],

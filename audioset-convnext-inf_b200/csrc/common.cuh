@@ -73,4 +73,47 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
 }
 
+// ---- tensor-core-path GELU on a register tile -----------------------------------------------------------------
+// 0.5 x (1 + tanh(x (a + b x^2 + c x^4))) with MUFU.TANH; (a, b, c) are a minimax re-fit against the EXACT erf GELU the
+// reference uses (nn.GELU(), convnext.py:65): max |err| 2.6e-5 over all x (textbook tanh-GELU: 4.7e-4), ~10x below the
+// bf16 rounding applied to the result; x^2 is clamped at 50 (tanh saturated) so the negative x^4 term cannot flip the
+// sign for |x| > 11.  Checked on the CPU by tests/test_host_logic.py::test_gelu_fit_against_exact_erf.
+// The tile is processed STAGE BY STAGE over all its pairs (packed fp32x2 FADD2/FMUL2/FFMA2 of sm_100): written pair by
+// pair the compiler serialised each pair's 8-deep dependency chain and the epilogue warps ran at ~0.15 IPC (ncu,
+// profiles/r01c); staged, the independent chains interleave.
+template <int NPAIR>
+__device__ __forceinline__ void bias_gelu_tile(const uint32_t* __restrict__ acc /*[2*NPAIR] fp32 bits*/,
+                                               const float* __restrict__ sbias /*smem*/, float2 (&out)[NPAIR]) {
+  float2 x[NPAIR], q[NPAIR];
+#pragma unroll
+  for (int i = 0; i < NPAIR; ++i)
+    x[i] = __fadd2_rn(make_float2(__uint_as_float(acc[2 * i]), __uint_as_float(acc[2 * i + 1])),
+                      *reinterpret_cast<const float2*>(sbias + 2 * i));
+#pragma unroll
+  for (int i = 0; i < NPAIR; ++i) q[i] = __fmul2_rn(x[i], x[i]);
+#pragma unroll
+  for (int i = 0; i < NPAIR; ++i) {
+    q[i].x = fminf(q[i].x, 50.0f);
+    q[i].y = fminf(q[i].y, 50.0f);
+  }
+#pragma unroll
+  for (int i = 0; i < NPAIR; ++i) {
+    const float2 p = __ffma2_rn(q[i], make_float2(-3.51516788e-04f, -3.51516788e-04f),
+                                make_float2(3.70056460e-02f, 3.70056460e-02f));
+    q[i] = __ffma2_rn(q[i], p, make_float2(7.97507884e-01f, 7.97507884e-01f));
+  }
+#pragma unroll
+  for (int i = 0; i < NPAIR; ++i) q[i] = __fmul2_rn(x[i], q[i]);
+#pragma unroll
+  for (int i = 0; i < NPAIR; ++i) {
+    asm("tanh.approx.f32 %0, %1;" : "=f"(q[i].x) : "f"(q[i].x));
+    asm("tanh.approx.f32 %0, %1;" : "=f"(q[i].y) : "f"(q[i].y));
+  }
+#pragma unroll
+  for (int i = 0; i < NPAIR; ++i) {
+    const float2 hx = __fmul2_rn(x[i], make_float2(0.5f, 0.5f));
+    out[i] = __ffma2_rn(hx, q[i], hx);
+  }
+}
+
 }  // namespace acx

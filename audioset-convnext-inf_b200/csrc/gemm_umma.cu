@@ -24,37 +24,6 @@ struct GemmArgs {
   int M, N, K;
 };
 
-// GELU for the bf16 tensor-core path: 0.5 x (1 + tanh(x (a + b x^2 + c x^4))) with MUFU.TANH.  (a, b, c)
-// are a minimax re-fit against the EXACT erf GELU the reference uses (nn.GELU(), convnext.py:65):
-// max |err| = 2.6e-5 over all x (textbook tanh-GELU: 4.7e-4), ~10x below the bf16 rounding applied to
-// the result.  x^2 is clamped at 50 (tanh already saturated) so the negative x^4 term cannot flip the
-// sign for |x| > 11.  Checked on the CPU by tests/test_host_logic.py::test_gelu_fit.
-__device__ __forceinline__ float gelu_fast(float x) {
-  const float x2 = fminf(x * x, 50.0f);
-  const float inner = x * fmaf(x2, fmaf(x2, -3.51516788e-04f, 3.70056460e-02f), 7.97507884e-01f);
-  float t;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(inner));
-  const float hx = 0.5f * x;
-  return fmaf(hx, t, hx);
-}
-
-// Two elements at a time with the packed fp32x2 pipe ops of sm_100 (FMUL2 / FFMA2): the polynomial and the final
-// blend cost one instruction per PAIR; only the clamp and MUFU.TANH stay scalar.
-__device__ __forceinline__ float2 gelu_fast2(float2 x) {
-  float2 x2 = __fmul2_rn(x, x);
-  x2.x = fminf(x2.x, 50.0f);
-  x2.y = fminf(x2.y, 50.0f);
-  const float2 p = __ffma2_rn(x2, make_float2(-3.51516788e-04f, -3.51516788e-04f),
-                              make_float2(3.70056460e-02f, 3.70056460e-02f));
-  const float2 q = __ffma2_rn(x2, p, make_float2(7.97507884e-01f, 7.97507884e-01f));
-  const float2 inner = __fmul2_rn(x, q);
-  float2 t;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(t.x) : "f"(inner.x));
-  asm("tanh.approx.f32 %0, %1;" : "=f"(t.y) : "f"(inner.y));
-  const float2 hx = __fmul2_rn(x, make_float2(0.5f, 0.5f));
-  return __ffma2_rn(hx, t, hx);
-}
-
 template <int BN_, int NEPI_>
 struct GemmCfg {
   static constexpr int BM = 128, BN = BN_, BK = 64, NEPI = NEPI_;
@@ -251,20 +220,22 @@ __global__ void __launch_bounds__(GemmCfg<BN, NEPI>::THREADS, 1)
           }
           const int n = n0 + (ch_begin + ci) * Cfg::CHUNK;
           float v[32];
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 b4 = *reinterpret_cast<const float4*>(sbias + n + j);
-            v[j + 0] = __uint_as_float(r[j + 0]) + b4.x;
-            v[j + 1] = __uint_as_float(r[j + 1]) + b4.y;
-            v[j + 2] = __uint_as_float(r[j + 2]) + b4.z;
-            v[j + 3] = __uint_as_float(r[j + 3]) + b4.w;
-          }
           if (EPI == ACX_EPI_BIAS_GELU) {
+            float2 o[16];
+            bias_gelu_tile<16>(r, sbias + n, o);
 #pragma unroll
-            for (int j = 0; j < 32; j += 2) {
-              const float2 o = gelu_fast2(make_float2(v[j], v[j + 1]));
-              v[j] = o.x;
-              v[j + 1] = o.y;
+            for (int j = 0; j < 16; ++j) {
+              v[2 * j] = o[j].x;
+              v[2 * j + 1] = o[j].y;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 b4 = *reinterpret_cast<const float4*>(sbias + n + j);
+              v[j + 0] = __uint_as_float(r[j + 0]) + b4.x;
+              v[j + 1] = __uint_as_float(r[j + 1]) + b4.y;
+              v[j + 2] = __uint_as_float(r[j + 2]) + b4.z;
+              v[j + 3] = __uint_as_float(r[j + 3]) + b4.w;
             }
           }
           if (EPI == ACX_EPI_BIAS_SCALE_RESID) {

@@ -14,8 +14,13 @@ namespace acx {
 // =============================================================================================
 // wave_prep
 // =============================================================================================
-template <bool kSplit>
-__global__ void wave_prep_kernel(const float* __restrict__ wave, void* __restrict__ hi_, void* __restrict__ lo_,
+// TIn = float (waveform) or int16_t (PCM as stored in the AudioSet HDF5 files; converted exactly like the reference's
+// int16_to_float32, utils/utilities.py:226-227: x / 32767. -- a true division, not a reciprocal multiply).
+__device__ __forceinline__ float load_sample(const float* p) { return __ldg(p); }
+__device__ __forceinline__ float load_sample(const int16_t* p) { return __fdiv_rn((float)__ldg(p), 32767.0f); }
+
+template <bool kSplit, typename TIn>
+__global__ void wave_prep_kernel(const TIn* __restrict__ wave, void* __restrict__ hi_, void* __restrict__ lo_,
                                  int L, int pad, int ld_pad) {
   const int b = blockIdx.y;
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -25,7 +30,7 @@ __global__ void wave_prep_kernel(const float* __restrict__ wave, void* __restric
     int s = j - pad;
     if (s < 0) s = -s;                       // reflect (edge sample not repeated)
     if (s >= L) s = 2 * (L - 1) - s;
-    v = __ldg(wave + (size_t)b * L + s);
+    v = load_sample(wave + (size_t)b * L + s);
   }
   const size_t o = (size_t)b * ld_pad + j;
   if (kSplit) {
@@ -608,24 +613,36 @@ static int dispatch_dwconv(const void* x, const void* w, const float* bias, cons
 
 using namespace acx;
 
-extern "C" {
-
-int acx_wave_prep(const float* wave, void* hi, void* lo, int B, int L, int n_fft, int ld_pad, int act_dtype,
-                  void* stream) {
+template <typename TIn>
+static int wave_prep_launch(const TIn* wave, void* hi, void* lo, int B, int L, int n_fft, int ld_pad, int act_dtype,
+                            void* stream) {
   ACX_CHECK(wave && hi && B > 0 && L > 0, ACX_ERR_ARG, "wave_prep: null pointer or empty batch");
   ACX_CHECK(L > n_fft / 2, ACX_ERR_ARG, "wave_prep: reflect padding needs L > n_fft/2 (L=%d)", L);
   ACX_CHECK(ld_pad >= L + n_fft && ld_pad % 8 == 0, ACX_ERR_ARG, "wave_prep: ld_pad=%d must be >= L+n_fft and %%8==0",
             ld_pad);
+  ACX_CHECK(B <= 65535, ACX_ERR_ARG, "wave_prep: batch %d exceeds gridDim.y", B);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   dim3 grid(ceil_div(ld_pad, 256), B);
   if (act_dtype == ACX_BF16) {
     ACX_CHECK(lo != nullptr, ACX_ERR_ARG, "wave_prep: lo buffer required for bf16 split");
-    wave_prep_kernel<true><<<grid, 256, 0, st>>>(wave, hi, lo, L, n_fft / 2, ld_pad);
+    wave_prep_kernel<true, TIn><<<grid, 256, 0, st>>>(wave, hi, lo, L, n_fft / 2, ld_pad);
   } else {
-    wave_prep_kernel<false><<<grid, 256, 0, st>>>(wave, hi, lo, L, n_fft / 2, ld_pad);
+    wave_prep_kernel<false, TIn><<<grid, 256, 0, st>>>(wave, hi, lo, L, n_fft / 2, ld_pad);
   }
   ACX_CUDA(cudaGetLastError());
   return ACX_OK;
+}
+
+extern "C" {
+
+int acx_wave_prep(const float* wave, void* hi, void* lo, int B, int L, int n_fft, int ld_pad, int act_dtype,
+                  void* stream) {
+  return wave_prep_launch<float>(wave, hi, lo, B, L, n_fft, ld_pad, act_dtype, stream);
+}
+
+int acx_wave_prep_pcm16(const int16_t* pcm, void* hi, void* lo, int B, int L, int n_fft, int ld_pad, int act_dtype,
+                        void* stream) {
+  return wave_prep_launch<int16_t>(pcm, hi, lo, B, L, n_fft, ld_pad, act_dtype, stream);
 }
 
 int acx_power_mel_log(const float* spec, int ld_spec, int n_bins, const float* melT, const int32_t* mel_lo,

@@ -20,21 +20,6 @@
 
 namespace acx {
 
-__device__ __forceinline__ float2 mlp_gelu2(float2 x) {   // see gemm_umma.cu::gelu_fast2
-  float2 x2 = __fmul2_rn(x, x);
-  x2.x = fminf(x2.x, 50.0f);
-  x2.y = fminf(x2.y, 50.0f);
-  const float2 p = __ffma2_rn(x2, make_float2(-3.51516788e-04f, -3.51516788e-04f),
-                              make_float2(3.70056460e-02f, 3.70056460e-02f));
-  const float2 q = __ffma2_rn(x2, p, make_float2(7.97507884e-01f, 7.97507884e-01f));
-  const float2 inner = __fmul2_rn(x, q);
-  float2 t;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(t.x) : "f"(inner.x));
-  asm("tanh.approx.f32 %0, %1;" : "=f"(t.y) : "f"(inner.y));
-  const float2 hx = __fmul2_rn(x, make_float2(0.5f, 0.5f));
-  return __ffma2_rn(hx, t, hx);
-}
-
 struct MlpArgs {
   bf16* x;            // residual stream, updated in place
   const float* b1;
@@ -285,14 +270,14 @@ __global__ void __launch_bounds__(384, 1)
         if (lane == 0) ptx::mbar_arrive(&d1_empty[buf]);          // D1 buffer free for GEMM1(h+2)
         const float* bias = sb1 + h * Cfg::NH + group * 64;
         uint32_t packed[32];
+        {
+          float2 o[16];
+          bias_gelu_tile<16>(ra, bias, o);
 #pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-          const float2 bA = *reinterpret_cast<const float2*>(bias + j);
-          const float2 bB = *reinterpret_cast<const float2*>(bias + 32 + j);
-          const float2 oA = mlp_gelu2(make_float2(__uint_as_float(ra[j]) + bA.x, __uint_as_float(ra[j + 1]) + bA.y));
-          const float2 oB = mlp_gelu2(make_float2(__uint_as_float(rb[j]) + bB.x, __uint_as_float(rb[j + 1]) + bB.y));
-          packed[j / 2] = Pair<bf16>::pack(oA.x, oA.y);
-          packed[16 + j / 2] = Pair<bf16>::pack(oB.x, oB.y);
+          for (int j = 0; j < 16; ++j) packed[j] = Pair<bf16>::pack(o[j].x, o[j].y);
+          bias_gelu_tile<16>(rb, bias + 32, o);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) packed[16 + j] = Pair<bf16>::pack(o[j].x, o[j].y);
         }
         ptx::mbar_wait(&h_empty[buf], par ^ 1);                   // GEMM2(h-2) finished reading this hidden buffer
         // this warp group's 64 hidden columns are k-block `group` of the hidden tile: one 128 B swizzled row per lane

@@ -260,11 +260,12 @@ class Engine:
     def _wave_prep(self, wave, ws, n, L, st):
         """Reads the caller's tensor -> stays outside any captured graph."""
         ld_pad = ws["ld_pad"]
+        fn = "acx_wave_prep_pcm16" if wave.dtype == torch.int16 else "acx_wave_prep"
         if self.frontend == "fused":
-            self._call("wave_prep", "acx_wave_prep", wave.data_ptr(), ws["wav_hi"].data_ptr(), ws["wav_lo"].data_ptr(),
+            self._call("wave_prep", fn, wave.data_ptr(), ws["wav_hi"].data_ptr(), ws["wav_lo"].data_ptr(),
                        n, L, N_FFT, ld_pad, N.ACX_BF16, st)
         else:
-            self._call("wave_prep", "acx_wave_prep", wave.data_ptr(), ws["wav_pad"].data_ptr(), 0, n, L, N_FFT, ld_pad,
+            self._call("wave_prep", fn, wave.data_ptr(), ws["wav_pad"].data_ptr(), 0, n, L, N_FFT, ld_pad,
                        N.ACX_F32, st)
 
     def _frontend(self, ws, n, L, st):
@@ -347,9 +348,10 @@ class Engine:
 
     # ---- public -----------------------------------------------------------------------------------
     def run(self, wave, want=("logits",)):
-        """wave: (B, L) float32 CUDA tensor.  want: subset of {"logits", "scene", "frame", "logmel"}.
+        """wave: (B, L) float32 CUDA tensor (or int16 PCM, converted x / 32767. on the fly).  want: subset of {"logits", "scene", "frame", "logmel"}.
         Returns dict of fp32 tensors: probs/logits (B,527), scene (B,768), frame (B,768,T',7)."""
-        assert wave.is_cuda and wave.dim() == 2 and wave.dtype == torch.float32 and wave.is_contiguous()
+        assert wave.is_cuda and wave.dim() == 2 and wave.is_contiguous()
+        assert wave.dtype in (torch.float32, torch.int16), "waveform must be float32 or int16 PCM"
         B, L = wave.shape
         T, hs = out_time_dims(L)
         if hs[3] < 1:

@@ -4,8 +4,8 @@ The reference's eval loop (`pytorch_utils.forward`, PU:88-137) does, per batch a
 `move_data_to_device(batch)` -> `model(batch)` -> `.data.cpu().numpy()`.  `HostPipeline` keeps that contract (host
 batches in, host results out, same order) but double-buffers: while the kernels of batch i run on the compute
 stream, batch i+1 is copied host->device on a copy stream and the result of batch i-1 is copied back.  Inputs may be
-fp32 waveforms or the int16 PCM the AudioSet HDF5 files store (`/32767` scaling of utilities.py:226-227 applied on
-the device), which halves the H2D bytes.
+fp32 waveforms or the int16 PCM the AudioSet HDF5 files store (`/32767.` of utilities.py:226-227 fused into the
+front end's first kernel), which halves the H2D bytes.
 """
 import torch
 
@@ -26,7 +26,6 @@ class HostPipeline:
         for _ in range(self.depth):
             slots.append(dict(
                 raw=torch.empty(B, L, device=self.dev, dtype=batch.dtype),
-                f32=torch.empty(B, L, device=self.dev, dtype=torch.float32) if batch.dtype != torch.float32 else None,
                 h2d=torch.cuda.Event(), done=torch.cuda.Event(), free=torch.cuda.Event(), out=None, host=None))
         self._slots = slots
         self._shape = (B, L, batch.dtype)
@@ -52,11 +51,7 @@ class HostPipeline:
                     s["raw"].copy_(hb, non_blocking=True)
                     s["h2d"].record(self.copy_stream)
                 compute.wait_event(s["h2d"])
-                x = s["raw"]
-                if s["f32"] is not None:                 # int16 PCM -> float (utilities.py:226-227: x / 32767.)
-                    torch.div(x, 32767.0, out=s["f32"])
-                    x = s["f32"]
-                out = self.eng.run(x, want=self.want)
+                out = self.eng.run(s["raw"], want=self.want)    # int16 PCM is converted inside acx_wave_prep_pcm16
                 s["free"].record(compute)
                 s["done"].record(compute)
                 with torch.cuda.stream(self.copy_stream):

@@ -56,6 +56,11 @@ ACX_API int acx_device_ok(void);
 ACX_API int acx_wave_prep(const float* wave, void* hi, void* lo, int B, int L, int n_fft, int ld_pad,
                   int act_dtype, void* stream);
 
+/* Same, reading int16 PCM (the AudioSet HDF5 storage format, reference utils/data_generator.py:70-74) and
+ * converting x / 32767. on the fly (utils/utilities.py:226-227): halves the H2D bytes of the eval loop. */
+ACX_API int acx_wave_prep_pcm16(const int16_t* pcm, void* hi, void* lo, int B, int L, int n_fft, int ld_pad,
+                        int act_dtype, void* stream);
+
 /* fp32-accurate path: spec (B*T, 2*n_bins) fp32 (re | im, from acx_gemm_f32 on the padded wave)
  * -> power -> mel (sparse band form) -> 10*log10(max(.,1e-10)) -> bn0 affine.
  * mel_lo/mel_hi (n_mels) int32 give each filter's non-zero bin range [lo, hi); melT is
