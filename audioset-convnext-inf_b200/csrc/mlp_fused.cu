@@ -14,6 +14,8 @@
 //   warps 4..11   epilogue-1 (TMEM -> +b1 -> GELU -> bf16 -> swizzled smem) per chunk, epilogue-2
 //            (TMEM -> +b2, *gamma, +residual -> bf16 -> TMA store) per tile
 // TMEM columns: D2 at 0 (C <= 192 -> 256 reserved), D1[0] at 256, D1[1] at 384.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "ptx.cuh"
 #include "tmap.cuh"
@@ -26,6 +28,8 @@ struct MlpArgs {
   const float* b2;
   const float* gamma;
   int M;
+  unsigned long long* trace;   // optional [16 tiles][2 roles][32 events] SM-clock stamps of CTA 0 (tools/trace_mlp.py)
+  int dbg;   // bring-up / A-B timing switches (ACX_DBG): 1 = skip GELU math, 2 = skip hidden-tile smem store
 };
 
 template <int C_>
@@ -373,6 +377,370 @@ __global__ void __launch_bounds__(384, 1)
   }
 }
 
+// =====================================================================================================================
+// C = 96 (stage 0, the largest M): WEIGHT-RESIDENT variant.  W1 (384 x 96) and W2 (96 x 384) are 144 KB of bf16 -- they
+// are TMA-loaded ONCE per persistent CTA and stay in shared memory, so the steady state streams only the y tile in and
+// the x tile out.  (The streaming variant above re-read 147 KB of weights from L2 per 128-row tile and, with a ring only
+// one hidden chunk deep, exposed one L2 round trip per chunk: 12.7 k cycles per tile against ~2.3 k of MMA work.)
+// K = 96 is split 64 + 32: the first 64 columns use 128B-swizzled tiles, the 32-column tail 64B-swizzled tiles, so no
+// shared memory is spent on zero padding (W1 48 + 24 KB, W2 72 KB, y tile 16 + 8 KB, hidden tile 32 KB).
+// =====================================================================================================================
+#define ACX_TRACE(role, ev)                                                                    \
+  do {                                                                                         \
+    if (a.trace && blockIdx.x == 0 && it < 16) a.trace[(it * 2 + (role)) * 32 + (ev)] = clock64(); \
+  } while (0)
+
+struct Mlp96 {
+  static constexpr int C = 96, HD = 384, BM = 128, NH = 128, NC = 3;
+  static constexpr int OFF_W1M = 0;                        // 3 x [128 rows x 64 k]  SW128   48 KB
+  static constexpr int OFF_W1T = OFF_W1M + 3 * 16384;      // 3 x [128 rows x 32 k]  SW64    24 KB
+  static constexpr int OFF_W2 = OFF_W1T + 3 * 8192;        // 6 x [ 96 rows x 64 k]  SW128   72 KB
+  static constexpr int OFF_AM = OFF_W2 + 6 * 12288;        // y tile [128 x 64] SW128        16 KB
+  static constexpr int OFF_AT = OFF_AM + 16384;            // y tile [128 x 32] SW64          8 KB
+  static constexpr int OFF_H = OFF_AT + 8192;              // hidden tile 2 x [128 x 64]     32 KB
+  static constexpr int OFF_STG = OFF_H + 32768;            // 8 warps x 2 KB                 16 KB
+  static constexpr int OFF_BAR = OFF_STG + 8 * 2048;
+  static constexpr int OFF_VEC = OFF_BAR + 256;
+  static constexpr int SMEM_BYTES = OFF_VEC + (HD + 2 * C) * 4 + 1024;
+  static constexpr int D2_COL = 0, D1_COL = 256, TMEM_COLS = 512;
+  static constexpr int W_BYTES = 3 * 16384 + 3 * 8192 + 6 * 12288;
+  static_assert(SMEM_BYTES <= 227 * 1024, "smem budget");
+};
+
+__global__ void __launch_bounds__(384, 1)
+    mlp_fused96_kernel(const __grid_constant__ CUtensorMap tmYm, const __grid_constant__ CUtensorMap tmYt,
+                       const __grid_constant__ CUtensorMap tmW1m, const __grid_constant__ CUtensorMap tmW1t,
+                       const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmOut, MlpArgs a) {
+  using Cfg = Mlp96;
+  constexpr int C = 96;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
+  uint64_t* w_full = bars;            // weights landed (once)
+  uint64_t* a_full = bars + 1;
+  uint64_t* a_empty = bars + 2;
+  uint64_t* d1_full = bars + 3;       // [2]
+  uint64_t* d1_empty = bars + 5;      // [2]
+  uint64_t* h_full = bars + 7;
+  uint64_t* h_empty = bars + 8;
+  uint64_t* d2_full = bars + 9;
+  uint64_t* d2_empty = bars + 10;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  float* sb1 = reinterpret_cast<float*>(smem + Cfg::OFF_VEC);
+  float* sb2 = sb1 + Cfg::HD;
+  float* sgamma = sb2 + C;
+  for (int i = threadIdx.x; i < Cfg::HD; i += blockDim.x) sb1[i] = a.b1[i];
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+    sb2[i] = a.b2[i];
+    sgamma[i] = a.gamma[i];
+  }
+  if (warp == 0 && ptx::elect_one()) {
+    ptx::prefetch_tensormap(&tmYm);
+    ptx::prefetch_tensormap(&tmYt);
+    ptx::prefetch_tensormap(&tmW1m);
+    ptx::prefetch_tensormap(&tmW1t);
+    ptx::prefetch_tensormap(&tmW2);
+    ptx::prefetch_tensormap(&tmOut);
+  }
+  if (warp == 1 && ptx::elect_one()) {
+    ptx::mbar_init(w_full, 1);
+    ptx::mbar_init(a_full, 1);
+    ptx::mbar_init(a_empty, 1);
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(&d1_full[s], 1);
+      ptx::mbar_init(&d1_empty[s], 8);
+    }
+    ptx::mbar_init(h_full, 8);
+    ptx::mbar_init(h_empty, 1);
+    ptx::mbar_init(d2_full, 1);
+    ptx::mbar_init(d2_empty, 8);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int num_tiles = (a.M + Cfg::BM - 1) / Cfg::BM;
+
+  if (warp == 0) {
+    // ===================== producer: weights once, then one y tile per row tile ==============================
+    if (ptx::elect_one()) {
+      ptx::mbar_arrive_expect_tx(w_full, Cfg::W_BYTES);
+      for (int h = 0; h < 3; ++h) {
+        ptx::tma_load_2d(smem + Cfg::OFF_W1M + h * 16384, &tmW1m, w_full, 0, h * 128);
+        ptx::tma_load_2d(smem + Cfg::OFF_W1T + h * 8192, &tmW1t, w_full, 64, h * 128);
+      }
+      for (int kb = 0; kb < 6; ++kb) ptx::tma_load_2d(smem + Cfg::OFF_W2 + kb * 12288, &tmW2, w_full, kb * 64, 0);
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        ptx::mbar_wait(a_empty, (it & 1) ^ 1);
+        ptx::mbar_arrive_expect_tx(a_full, 16384 + 8192);
+        ptx::tma_load_2d(smem + Cfg::OFF_AM, &tmYm, a_full, 0, tile * Cfg::BM);
+        ptx::tma_load_2d(smem + Cfg::OFF_AT, &tmYt, a_full, 64, tile * Cfg::BM);
+        const int next = tile + gridDim.x;                        // the single y buffer cannot be loaded ahead, but
+        if (next < num_tiles) {                                   // its HBM latency can: pull the next tile into L2
+          ptx::tma_prefetch_2d(&tmYm, 0, next * Cfg::BM);
+          ptx::tma_prefetch_2d(&tmYt, 64, next * Cfg::BM);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer ========================================================================
+    if (ptx::elect_one()) {
+      constexpr uint32_t idesc1 = ptx::umma_idesc_bf16(Cfg::BM, Cfg::NH);
+      constexpr uint32_t idesc2 = ptx::umma_idesc_bf16(Cfg::BM, C);
+      const uint32_t d2 = tmem_base + Cfg::D2_COL;
+      const uint32_t sbase = ptx::smem_u32(smem);
+      const uint64_t dAm = ptx::umma_desc_sw128_kmajor(sbase + Cfg::OFF_AM);
+      const uint64_t dAt = ptx::umma_desc_sw64_kmajor(sbase + Cfg::OFF_AT);
+      ptx::mbar_wait(w_full, 0);
+      ptx::tc_fence_after();
+      int it = 0;
+      uint32_t gc = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        auto gemm2 = [&](int hh, uint32_t gch) {
+          ptx::mbar_wait(h_full, gch & 1);
+          if (hh == 0) ptx::mbar_wait(d2_empty, (it & 1) ^ 1);
+          ptx::tc_fence_after();
+#pragma unroll
+          for (int kb = 0; kb < 2; ++kb) {
+            const uint64_t da = ptx::umma_desc_sw128_kmajor(sbase + Cfg::OFF_H + kb * 16384);
+            const uint64_t db = ptx::umma_desc_sw128_kmajor(sbase + Cfg::OFF_W2 + (hh * 2 + kb) * 12288);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) ptx::umma_bf16(d2, da + 2 * k, db + 2 * k, idesc2, (hh | kb | k) != 0 ? 1u : 0u);
+          }
+          ptx::umma_commit(h_empty);
+        };
+        ACX_TRACE(0, 0);
+        ptx::mbar_wait(a_full, it & 1);
+        ptx::tc_fence_after();
+        ACX_TRACE(0, 1);
+        for (int h = 0; h < Cfg::NC; ++h, ++gc) {
+          const int db1 = gc & 1;
+          ptx::mbar_wait(&d1_empty[db1], ((gc >> 1) & 1) ^ 1);
+          ptx::tc_fence_after();
+          ACX_TRACE(0, 2 + 3 * h);
+          const uint32_t d1 = tmem_base + Cfg::D1_COL + db1 * Cfg::NH;
+          const uint64_t dBm = ptx::umma_desc_sw128_kmajor(sbase + Cfg::OFF_W1M + h * 16384);
+          const uint64_t dBt = ptx::umma_desc_sw64_kmajor(sbase + Cfg::OFF_W1T + h * 8192);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) ptx::umma_bf16(d1, dAm + 2 * k, dBm + 2 * k, idesc1, k != 0 ? 1u : 0u);
+#pragma unroll
+          for (int k = 0; k < 2; ++k) ptx::umma_bf16(d1, dAt + 2 * k, dBt + 2 * k, idesc1, 1u);
+          ptx::umma_commit(&d1_full[db1]);
+          ACX_TRACE(0, 3 + 3 * h);
+          if (h == Cfg::NC - 1) ptx::umma_commit(a_empty);
+          if (h >= 1) gemm2(h - 1, gc - 1);
+          ACX_TRACE(0, 4 + 3 * h);
+        }
+        gemm2(Cfg::NC - 1, gc - 1);
+        ptx::umma_commit(d2_full);
+        ACX_TRACE(0, 11);
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue warps ====================================================================
+    const int ew = warp - 4;
+    const int quad = warp & 3;
+    const int group = ew >> 2;
+    const int row_in_tile = quad * 32 + lane;
+    const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+    uint8_t* stg = smem + Cfg::OFF_STG + ew * 2048;
+    const bool tr = (warp == 4 && lane == 0);
+    const int sw64 = (lane >> 1) & 3;
+    const int ld_piece = lane & 3, ld_row = lane >> 2;
+    int it = 0;
+    uint32_t gc = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      {  // the residual rows of this tile are needed only by epilogue-2: start their HBM -> L2 trip now
+        const int pr = tile * Cfg::BM + (ew * 32 + lane) / 2;     // 256 threads x 96 B cover 128 rows x 192 B
+        if (pr < a.M) ptx::prefetch_l2(a.x + (size_t)pr * C + ((ew * 32 + lane) & 1) * 48);
+      }
+      for (int h = 0; h < Cfg::NC; ++h, ++gc) {
+        const int buf = gc & 1;
+        if (tr) ACX_TRACE(1, 4 * h);
+        ptx::mbar_wait_backoff(&d1_full[buf], (gc >> 1) & 1);
+        ptx::tc_fence_after();
+        if (tr) ACX_TRACE(1, 4 * h + 1);
+        const uint32_t t0 = lane_base + Cfg::D1_COL + buf * Cfg::NH + group * 64;
+        uint32_t ra[32], rb[32];
+        ptx::tmem_ld_32x32b_x32(t0, ra);
+        ptx::tmem_ld_32x32b_x32(t0 + 32, rb);
+        ptx::tmem_ld_wait();
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&d1_empty[buf]);
+        if (tr) ACX_TRACE(1, 4 * h + 2);
+        const float* bias = sb1 + h * Cfg::NH + group * 64;
+        uint32_t packed[32];
+        if (a.dbg & 1) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            packed[j] = Pair<bf16>::pack(__uint_as_float(ra[2 * j]), __uint_as_float(ra[2 * j + 1]));
+            packed[16 + j] = Pair<bf16>::pack(__uint_as_float(rb[2 * j]), __uint_as_float(rb[2 * j + 1]));
+          }
+        } else {
+          float2 o[16];
+          bias_gelu_tile<16>(ra, bias, o);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) packed[j] = Pair<bf16>::pack(o[j].x, o[j].y);
+          bias_gelu_tile<16>(rb, bias + 32, o);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) packed[16 + j] = Pair<bf16>::pack(o[j].x, o[j].y);
+        }
+        if (tr && h == 0) ACX_TRACE(1, 22);
+        ptx::mbar_wait(h_empty, (gc & 1) ^ 1);                    // GEMM2 of the previous chunk has read the hidden tile
+        if (tr && h == 0) ACX_TRACE(1, 23);
+        uint8_t* hrow = smem + Cfg::OFF_H + group * 16384 + row_in_tile * 128;
+        if (!(a.dbg & 2)) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            *reinterpret_cast<uint4*>(hrow + ((q ^ (row_in_tile & 7)) << 4)) =
+                make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
+        } else if (packed[0] == 0x12345678u) {
+          *reinterpret_cast<uint32_t*>(hrow) = packed[lane & 31];
+        }
+        if (tr && h == 0) ACX_TRACE(1, 24);
+        ptx::fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(h_full);
+        if (tr) ACX_TRACE(1, 4 * h + 3);
+      }
+      // ---- epilogue-2: 3 output chunks of 32 columns: group 0 takes chunks 0,1; group 1 takes chunk 2 ----------
+      const int row0 = tile * Cfg::BM + quad * 32;
+      const int ch_begin = group == 0 ? 0 : 2;
+      const int ch_count = group == 0 ? 2 : 1;
+      uint4 rq[4];
+      auto fetch_resid = [&](int ci) {
+        const int n = (ch_begin + ci) * 32;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int r = row0 + ld_row + 8 * q;
+          rq[q] = make_uint4(0u, 0u, 0u, 0u);
+          if (r < a.M) rq[q] = *reinterpret_cast<const uint4*>(a.x + (size_t)r * C + n + ld_piece * 8);
+        }
+      };
+      fetch_resid(0);
+      ptx::mbar_wait_backoff(d2_full, it & 1);
+      ptx::tc_fence_after();
+      if (tr) ACX_TRACE(1, 12);
+#pragma unroll
+      for (int ci = 0; ci < 2; ++ci) {
+        if (ci < ch_count) {
+          const int n = (ch_begin + ci) * 32;
+          uint32_t r[32];
+          ptx::tmem_ld_32x32b_x32(lane_base + Cfg::D2_COL + n, r);
+          ptx::tmem_ld_wait();
+          if (tr) ACX_TRACE(1, 13 + ci);
+          if (ci + 1 == ch_count) {
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(d2_empty);
+          }
+          if (lane == 0) ptx::tma_store_wait_read<0>();
+          __syncwarp();
+          if (tr && ci == 0) ACX_TRACE(1, 16);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int rr = ld_row + 8 * q;
+            *reinterpret_cast<uint4*>(stg + rr * 64 + ((ld_piece ^ ((rr >> 1) & 3)) << 4)) = rq[q];
+          }
+          __syncwarp();
+          if (tr && ci == 0) ACX_TRACE(1, 17);
+          uint4 res[4];
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) res[j4] = *reinterpret_cast<const uint4*>(stg + lane * 64 + ((j4 ^ sw64) << 4));
+          __syncwarp();
+          if (ci + 1 < ch_count) fetch_resid(ci + 1);
+          if (tr && ci == 0) ACX_TRACE(1, 18);
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const int j = j4 * 8;
+            const float4 bA = *reinterpret_cast<const float4*>(sb2 + n + j);
+            const float4 bB = *reinterpret_cast<const float4*>(sb2 + n + j + 4);
+            const float4 gA = *reinterpret_cast<const float4*>(sgamma + n + j);
+            const float4 gB = *reinterpret_cast<const float4*>(sgamma + n + j + 4);
+            float2 f;
+            uint4 o;
+            f = Pair<bf16>::unpack(res[j4].x);
+            o.x = Pair<bf16>::pack(fmaf(gA.x, __uint_as_float(r[j + 0]) + bA.x, f.x), fmaf(gA.y, __uint_as_float(r[j + 1]) + bA.y, f.y));
+            f = Pair<bf16>::unpack(res[j4].y);
+            o.y = Pair<bf16>::pack(fmaf(gA.z, __uint_as_float(r[j + 2]) + bA.z, f.x), fmaf(gA.w, __uint_as_float(r[j + 3]) + bA.w, f.y));
+            f = Pair<bf16>::unpack(res[j4].z);
+            o.z = Pair<bf16>::pack(fmaf(gB.x, __uint_as_float(r[j + 4]) + bB.x, f.x), fmaf(gB.y, __uint_as_float(r[j + 5]) + bB.y, f.y));
+            f = Pair<bf16>::unpack(res[j4].w);
+            o.w = Pair<bf16>::pack(fmaf(gB.z, __uint_as_float(r[j + 6]) + bB.z, f.x), fmaf(gB.w, __uint_as_float(r[j + 7]) + bB.w, f.y));
+            *reinterpret_cast<uint4*>(stg + lane * 64 + ((j4 ^ sw64) << 4)) = o;
+          }
+          if (tr && ci == 0) ACX_TRACE(1, 19);
+          ptx::fence_proxy_async_smem();
+          __syncwarp();
+          if (tr && ci == 0) ACX_TRACE(1, 20);
+          if (lane == 0) {
+            ptx::tma_store_2d(&tmOut, stg, n, row0);
+            ptx::tma_store_commit();
+          }
+          if (tr && ci == 0) ACX_TRACE(1, 21);
+        }
+      }
+      if (tr) ACX_TRACE(1, 15);
+    }
+    if (lane == 0) ptx::tma_store_wait_read<0>();
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+static int launch_mlp96_resident(const void* y, void* x, const void* w1, const float* b1, const void* w2,
+                                 const float* b2, const float* gamma, int M, cudaStream_t st) {
+  using Cfg = Mlp96;
+  CUtensorMap tmYm, tmYt, tmW1m, tmW1t, tmW2, tmOut;
+  int rc = make_tmap_2d_bf16(&tmYm, y, 96, (uint64_t)M, 192, 64, 128);
+  if (rc != ACX_OK) return rc;
+  rc = make_tmap_2d_bf16(&tmYt, y, 96, (uint64_t)M, 192, 32, 128, CU_TENSOR_MAP_SWIZZLE_64B);
+  if (rc != ACX_OK) return rc;
+  rc = make_tmap_2d_bf16(&tmW1m, w1, 96, 384, 192, 64, 128);
+  if (rc != ACX_OK) return rc;
+  rc = make_tmap_2d_bf16(&tmW1t, w1, 96, 384, 192, 32, 128, CU_TENSOR_MAP_SWIZZLE_64B);
+  if (rc != ACX_OK) return rc;
+  rc = make_tmap_2d_bf16(&tmW2, w2, 384, 96, 768, 64, 96);
+  if (rc != ACX_OK) return rc;
+  rc = make_tmap_2d_bf16(&tmOut, x, 96, (uint64_t)M, 192, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
+  if (rc != ACX_OK) return rc;
+  static bool configured = false;
+  if (!configured) {
+    ACX_CUDA(cudaFuncSetAttribute(mlp_fused96_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    configured = true;
+  }
+  int dev = 0, sms = 0;
+  ACX_CUDA(cudaGetDevice(&dev));
+  ACX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int tiles = ceil_div(M, Cfg::BM);
+  MlpArgs a;
+  a.x = reinterpret_cast<bf16*>(x);
+  a.b1 = b1;
+  a.b2 = b2;
+  a.gamma = gamma;
+  a.M = M;
+  a.dbg = getenv("ACX_DBG") ? atoi(getenv("ACX_DBG")) : 0;
+  a.trace = getenv("ACX_TRACE_PTR") ? reinterpret_cast<unsigned long long*>(strtoull(getenv("ACX_TRACE_PTR"), nullptr, 0)) : nullptr;
+  mlp_fused96_kernel<<<tiles < sms ? tiles : sms, 384, Cfg::SMEM_BYTES, st>>>(tmYm, tmYt, tmW1m, tmW1t, tmW2, tmOut, a);
+  ACX_CUDA(cudaGetLastError());
+  return ACX_OK;
+}
+
 template <int C>
 static int launch_mlp(const void* y, void* x, const void* w1, const float* b1, const void* w2, const float* b2,
                       const float* gamma, int M, cudaStream_t st) {
@@ -402,6 +770,8 @@ static int launch_mlp(const void* y, void* x, const void* w1, const float* b1, c
   a.b2 = b2;
   a.gamma = gamma;
   a.M = M;
+  a.dbg = 0;
+  a.trace = nullptr;
   kern<<<tiles < sms ? tiles : sms, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(tmY, tmW1, tmW2, tmOut, a);
   ACX_CUDA(cudaGetLastError());
   return ACX_OK;
@@ -420,7 +790,10 @@ extern "C" int acx_mlp_fused(const void* y, void* x, const void* w1, const float
             ACX_ERR_ARG, "mlp_fused: y, x, w1 and w2 must be 16-byte aligned");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   switch (C) {
-    case 96: return launch_mlp<96>(y, x, w1, b1, w2, b2, gamma, M, st);
+    case 96:
+      // weight-resident kernel; the streaming variant stays reachable for A/B timing (ACX_MLP96_STREAM=1)
+      if (getenv("ACX_MLP96_STREAM")) return launch_mlp<96>(y, x, w1, b1, w2, b2, gamma, M, st);
+      return launch_mlp96_resident(y, x, w1, b1, w2, b2, gamma, M, st);
     case 192: return launch_mlp<192>(y, x, w1, b1, w2, b2, gamma, M, st);
     default:
       set_error("mlp_fused: C=%d not supported (the fused kernel covers stages 0-1: C = 96, 192; wider stages exceed "

@@ -47,35 +47,35 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Watchdog: a mis-programmed pipeline must trap (sticky CUDA error) instead of hanging the GPU.
+// Blocking wait.  try_wait carries a suspend-time hint, so a waiting thread SLEEPS in hardware until the phase flips
+// (or the hint expires) instead of spinning: a tight try_wait/branch loop in the single-thread producer / MMA warps
+// stole issue slots from the epilogue warps sharing their scheduler and slowed every epilogue step ~5x (in-kernel
+// clock trace, tools/trace_mlp.py).  Watchdog: a mis-programmed pipeline traps (sticky CUDA error) instead of hanging.
 #ifndef ACX_MBAR_SPIN_LIMIT
-#define ACX_MBAR_SPIN_LIMIT (1u << 28)
+#define ACX_MBAR_SPIN_LIMIT 4000u      /* x 10 ms hint */
 #endif
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t ticks) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(ticks)
+      : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
+  while (!mbar_try_wait_hint(bar, parity, 0x989680u)) {
     if (++spins > ACX_MBAR_SPIN_LIMIT) {
-      printf("acx: mbarrier watchdog block=%d thread=%d bar=%u parity=%u\n", (int)blockIdx.x,
-             (int)threadIdx.x, smem_u32(bar), parity);
+      printf("acx: mbarrier watchdog block=%d thread=%d bar=%u parity=%u\n", (int)blockIdx.x, (int)threadIdx.x,
+             smem_u32(bar), parity);
       __trap();
     }
   }
 }
-
-// Same, for waits that are expected to be long (epilogue warps waiting for an accumulator): back off between
-// polls so the spinning warp does not steal issue slots from the warps that are computing on the same scheduler.
-__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  uint32_t spins = 0;
-  do {
-    __nanosleep(64);
-    if (++spins > (ACX_MBAR_SPIN_LIMIT >> 4)) {
-      printf("acx: mbarrier watchdog (backoff) block=%d thread=%d bar=%u parity=%u\n", (int)blockIdx.x,
-             (int)threadIdx.x, smem_u32(bar), parity);
-      __trap();
-    }
-  } while (!mbar_try_wait(bar, parity));
-}
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) { mbar_wait(bar, parity); }
 
 // generic-proxy smem writes -> visible to the async proxy (TMA / tcgen05.mma reads)
 __device__ __forceinline__ void fence_proxy_async_smem() {
@@ -109,6 +109,16 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* t
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1),
       "r"(c2), "r"(c3)
       : "memory");
+}
+
+// Pull a tile / a line into L2 ahead of its use (no smem, no barrier).
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* tm, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(tm)),
+               "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
 
 // smem -> global tile store (bulk async group); rows/cols outside the tensor are clipped by the TMA unit.
@@ -197,6 +207,16 @@ __device__ __forceinline__ uint64_t umma_desc_sw128_kmajor(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(1024 >> 4) << 32;       // SBO: 8 rows * 128 B
   d |= static_cast<uint64_t>(1) << 46;               // descriptor version
   d |= static_cast<uint64_t>(2) << 61;               // SWIZZLE_128B
+  return d;
+}
+// Same for a 32-element-wide (64 B rows) K-major tile laid out with SWIZZLE_64B: 8-row atoms 512 B apart.
+__device__ __forceinline__ uint64_t umma_desc_sw64_kmajor(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(512 >> 4) << 32;        // SBO: 8 rows * 64 B
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(4) << 61;               // SWIZZLE_64B
   return d;
 }
 // Instruction descriptor, kind::f16: A = B = bf16 (K-major), D = fp32, tile M x N.
