@@ -145,7 +145,7 @@ class Engine:
         self.w = PackedWeights(state_dict, self.device, precision)
         self.adt = N.ACX_BF16 if precision == "bf16" else N.ACX_F32
         self.esize = 2 if precision == "bf16" else 4
-        self.chunk = int(chunk or os.environ.get("ACX_CHUNK", 32 if precision == "bf16" else 4))
+        self.chunk = int(chunk or os.environ.get("ACX_CHUNK", 64 if precision == "bf16" else 4))
         # which implementation of the two fusable pieces to run (both are libacx kernels)
         self.frontend = frontend or os.environ.get("ACX_FRONTEND", "fused" if precision == "bf16" else "simt")
         self.mlp = mlp or os.environ.get("ACX_MLP", "fused")
