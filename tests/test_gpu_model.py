@@ -153,3 +153,46 @@ def test_host_pipeline_matches_direct_calls(models):
         ref_wave = (p.numpy() / 32767.0).astype("float32")        # utilities.py:226-227, on the host
         d = m(torch.from_numpy(ref_wave).to(DEV))
         assert torch.equal(r["logits"], d["clipwise_logits"].cpu())
+
+
+def test_eval_loop_drop_in_matches_reference_loop_semantics(models, parity_sd):
+    """evalloop.forward == the reference's pytorch_utils.forward (PU:63-137): per batch model(x)['clipwise_output'],
+    concatenated; accepts the collate_fn's dtype=object arrays and int16 PCM."""
+    from audioset_convnext_inf_b200 import evalloop
+    m = models["fp32"]
+    L = 32000
+    waves = weights.make_waveforms(7, n_samples=L, kind="noise", seed=33)
+    obj = np.empty(3, dtype=object)
+    for i in range(3):
+        obj[i] = waves[4 + i].numpy()
+    gen = [{"waveform": waves[:4].numpy(), "target": np.zeros((4, 527), np.float32)},
+           {"waveform": obj, "target": np.ones((3, 527), np.float32)}]
+    out = evalloop.forward(m, gen, return_input=True, return_target=True)
+    assert out["clipwise_output"].shape == (7, 527) and out["target"].shape == (7, 527) and out["waveform"].shape == (7, L)
+    ref = O.forward(waves, parity_sd)["clipwise_output"].numpy()       # what the reference loop would return
+    assert np.abs(out["clipwise_output"] - ref).max() < 1e-4
+    direct = torch.cat([m(waves[:4].to(DEV))["clipwise_output"], m(waves[4:].to(DEV))["clipwise_output"]]).cpu().numpy()
+    assert np.array_equal(out["clipwise_output"], direct)
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_edge_shapes(models, prec):
+    """B=1, batch larger than the chunk, the shortest clip the 4-stage trunk accepts, non-contiguous input."""
+    m = models[prec]
+    eng = m._get_engine()
+    L = 16000
+    w = weights.make_waveforms(eng.chunk + 3 if prec == "fp32" else 5, n_samples=L, kind="noise", seed=50).to(DEV)
+    full = m(w)["clipwise_logits"]
+    one = m(w[1:2])["clipwise_logits"]
+    assert torch.equal(full[1], one[0])
+    nc = torch.stack([w, w], 2)[:, :, 0]                              # non-contiguous view
+    assert not nc.is_contiguous()
+    assert torch.equal(m(nc)["clipwise_logits"], full)
+    short = weights.make_waveforms(2, n_samples=7 * 320 * 4 + 1, kind="noise", seed=51).to(DEV)   # T'=1 at stage 3
+    fr = m.forward_frame_embeddings(short)
+    ref = O.forward_frame_embeddings(short.cpu(), weights.make_state_dict("parity", 8))
+    assert fr.shape == ref.shape and fr.shape[2] >= 1
+    with pytest.raises(ValueError):
+        m(torch.zeros(1, 2000, device=DEV))                          # too short for the trunk
+    with pytest.raises(ValueError):
+        m(torch.zeros(320000, device=DEV))                           # not (batch, samples)
