@@ -10,6 +10,8 @@
 //
 // Used for pwconv1+GELU / pwconv2+gamma+residual (reference convnext.py:79-86) and the 2x2/s2 downsample
 // convolutions as GEMMs over the patch matrix (convnext.py:231-234).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "ptx.cuh"
 #include "tmap.cuh"
@@ -24,14 +26,19 @@ struct GemmArgs {
   int M, N, K;
 };
 
-template <int BN_, int NEPI_>
+// CG = 1: one CTA per 128 x BN tile.  CG = 2: a CTA PAIR (cluster of 2, tcgen05 cta_group::2) per 256 x BN tile -- each
+// CTA stages its own 128 A rows and HALF of the B rows, so operand traffic from L2 per FLOP drops by a third and the
+// smaller stage allows a deeper ring.  The stage-2/3 GEMMs were L2-bandwidth-bound with CG = 1 (ncu: tensor pipe 50 %,
+// ~10 TB/s of operand re-reads).
+template <int BN_, int NEPI_, int CG_ = 1>
 struct GemmCfg {
-  static constexpr int BM = 128, BN = BN_, BK = 64, NEPI = NEPI_;
+  static constexpr int BM = 128, BN = BN_, BK = 64, NEPI = NEPI_, CG = CG_;
   static constexpr int A_BYTES = BM * BK * 2;
-  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int B_BYTES = (BN / CG) * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES_RAW = (160 * 1024) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 6 ? 6 : STAGES_RAW;
+  static_assert(CG == 1 || BN % 32 == 0, "B halves");
   static constexpr int ACC_STRIDE = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
   static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
   // epilogue: 8 warps = 4 TMEM lane quadrants x 2 column groups; columns are handed out in chunks of 32
@@ -53,11 +60,14 @@ struct GemmCfg {
   static_assert(SMEM_BYTES <= 227 * 1024, "smem budget");
 };
 
-template <int BN, int EPI, int NEPI>
-__global__ void __launch_bounds__(GemmCfg<BN, NEPI>::THREADS, 1)
+template <int BN, int EPI, int NEPI, int CG>
+__global__ void __launch_bounds__(GemmCfg<BN, NEPI, CG>::THREADS, 1)
     umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const __grid_constant__ CUtensorMap tmOut, GemmArgs g) {
-  using Cfg = GemmCfg<BN, NEPI>;
+  using Cfg = GemmCfg<BN, NEPI, CG>;
+  const uint32_t cta_rank = CG == 2 ? ptx::cluster_ctarank() : 0u;   // 0 = leader of the pair
+  const int unit = CG == 2 ? blockIdx.x >> 1 : blockIdx.x;           // persistent work unit (CTA or CTA pair)
+  const int num_units = CG == 2 ? gridDim.x >> 1 : gridDim.x;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
@@ -89,20 +99,26 @@ __global__ void __launch_bounds__(GemmCfg<BN, NEPI>::THREADS, 1)
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&tfull_bar[a], 1);
-      ptx::mbar_init(&tempty_bar[a], NEPI);
+      ptx::mbar_init(&tempty_bar[a], NEPI * CG);   // the leader's copy collects the epilogue warps of both CTAs
     }
     ptx::fence_barrier_init();
   }
   if (warp == 2) {
-    ptx::tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
-    ptx::tmem_relinquish();
+    if (CG == 2) {
+      ptx::tmem_alloc_cg2(tmem_slot, Cfg::TMEM_COLS);
+      ptx::tmem_relinquish_cg2();
+    } else {
+      ptx::tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+      ptx::tmem_relinquish();
+    }
   }
   ptx::tc_fence_before();
   __syncthreads();
+  if (CG == 2) ptx::cluster_sync_all();            // peer barriers are initialised before any remote arrive / TMA
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int num_m_tiles = (g.M + Cfg::BM - 1) / Cfg::BM;
+  const int num_m_tiles = (g.M + Cfg::BM * CG - 1) / (Cfg::BM * CG);   // tiles of 128 (CG=1) or 256 (CG=2) rows
   const int num_n_tiles = g.N / BN;
   const int num_tiles = num_m_tiles * num_n_tiles;
   const int num_kb = (g.K + Cfg::BK - 1) / Cfg::BK;
@@ -112,16 +128,23 @@ __global__ void __launch_bounds__(GemmCfg<BN, NEPI>::THREADS, 1)
     if (ptx::elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / num_n_tiles) * Cfg::BM;
-        const int n0 = (tile % num_n_tiles) * BN;
+      for (int tile = unit; tile < num_tiles; tile += num_units) {
+        const int m0 = (tile / num_n_tiles) * Cfg::BM * CG + cta_rank * Cfg::BM;
+        const int n0 = (tile % num_n_tiles) * BN + cta_rank * (BN / CG);
         for (int kb = 0; kb < num_kb; ++kb) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + Cfg::A_BYTES;
-          ptx::mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-          ptx::tma_load_2d(sa, &tmA, &full_bar[stage], kb * Cfg::BK, m0);
-          ptx::tma_load_2d(sb, &tmB, &full_bar[stage], kb * Cfg::BK, n0);
+          if (CG == 2) {
+            // both CTAs' bytes complete on the LEADER's full barrier; only the leader arms it
+            if (cta_rank == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+            ptx::tma_load_2d_cg2(sa, &tmA, &full_bar[stage], kb * Cfg::BK, m0);
+            ptx::tma_load_2d_cg2(sb, &tmB, &full_bar[stage], kb * Cfg::BK, n0);
+          } else {
+            ptx::mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+            ptx::tma_load_2d(sa, &tmA, &full_bar[stage], kb * Cfg::BK, m0);
+            ptx::tma_load_2d(sb, &tmB, &full_bar[stage], kb * Cfg::BK, n0);
+          }
           if (++stage == Cfg::STAGES) {
             stage = 0;
             phase ^= 1;
@@ -130,13 +153,13 @@ __global__ void __launch_bounds__(GemmCfg<BN, NEPI>::THREADS, 1)
       }
     }
   } else if (warp == 1) {
-    // ================================ MMA issuer ==================================
-    if (ptx::elect_one()) {
-      constexpr uint32_t idesc = ptx::umma_idesc_bf16(Cfg::BM, BN);
+    // ================================ MMA issuer (leader CTA only when paired) ==================================
+    if (cta_rank == 0 && ptx::elect_one()) {
+      constexpr uint32_t idesc = ptx::umma_idesc_bf16(Cfg::BM * CG, BN);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      for (int tile = unit; tile < num_tiles; tile += num_units, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
         ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
@@ -152,16 +175,20 @@ __global__ void __launch_bounds__(GemmCfg<BN, NEPI>::THREADS, 1)
           for (int k = 0; k < Cfg::BK / 16; ++k) {
             if (kb * Cfg::BK + k * 16 < g.K) {
               // advance 16 bf16 = 32 B along K inside the 128B swizzle row: +2 in the (addr >> 4) field
-              ptx::umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+              if (CG == 2) ptx::umma_bf16_cg2(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+              else ptx::umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
             }
           }
-          ptx::umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
+          // smem slot reusable (in both CTAs when paired) once these MMAs retire
+          if (CG == 2) ptx::umma_commit_cg2(&empty_bar[stage]);
+          else ptx::umma_commit(&empty_bar[stage]);
           if (++stage == Cfg::STAGES) {
             stage = 0;
             phase ^= 1;
           }
         }
-        ptx::umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+        if (CG == 2) ptx::umma_commit_cg2(&tfull_bar[acc]);  // accumulator complete -> epilogue warps of both CTAs
+        else ptx::umma_commit(&tfull_bar[acc]);
       }
     }
   } else if (warp >= 4) {
@@ -181,10 +208,10 @@ __global__ void __launch_bounds__(GemmCfg<BN, NEPI>::THREADS, 1)
     const int ld_piece = lane & 3, ld_row = lane >> 2;   // coalesced residual fetch: 4 pieces x 8 rows per instruction
     int it = 0;
     uint32_t store_parity = 0;            // which staging tile the next chunk uses
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    for (int tile = unit; tile < num_tiles; tile += num_units, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      const int m0 = (tile / num_n_tiles) * Cfg::BM;
+      const int m0 = (tile / num_n_tiles) * Cfg::BM * CG + cta_rank * Cfg::BM;
       const int n0 = (tile % num_n_tiles) * BN;
       const int row0 = m0 + quad * 32;
       uint4 rq[4];
@@ -216,7 +243,10 @@ __global__ void __launch_bounds__(GemmCfg<BN, NEPI>::THREADS, 1)
             // last TMEM read of this accumulator has landed: hand it back to the MMA warp
             ptx::tc_fence_before();
             __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
+            if (lane == 0) {
+              if (CG == 2) ptx::mbar_arrive_leader(&tempty_bar[acc]);
+              else ptx::mbar_arrive(&tempty_bar[acc]);
+            }
           }
           const int n = n0 + (ch_begin + ci) * Cfg::CHUNK;
           float v[32];
@@ -290,17 +320,19 @@ __global__ void __launch_bounds__(GemmCfg<BN, NEPI>::THREADS, 1)
 
   ptx::tc_fence_before();
   __syncthreads();
+  if (CG == 2) ptx::cluster_sync_all();            // the peer may still multicast into / read from this CTA's smem
   if (warp == 2) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    if (CG == 2) ptx::tmem_dealloc_cg2(tmem_base, Cfg::TMEM_COLS);
+    else ptx::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
 }
 
-template <int BN, int EPI, int NEPI>
+template <int BN, int EPI, int NEPI, int CG>
 static int launch_umma_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut, const GemmArgs& g,
                             cudaStream_t st) {
-  using Cfg = GemmCfg<BN, NEPI>;
-  auto kern = umma_gemm_kernel<BN, EPI, NEPI>;
+  using Cfg = GemmCfg<BN, NEPI, CG>;
+  auto kern = umma_gemm_kernel<BN, EPI, NEPI, CG>;
   static bool configured = false;  // per-instantiation; benign race (idempotent attribute set)
   if (!configured) {
     ACX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
@@ -308,41 +340,59 @@ static int launch_umma_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, cons
   }
   ACX_CHECK(g.N * (EPI == ACX_EPI_BIAS_SCALE_RESID ? 8 : 4) <= Cfg::VEC_BYTES, ACX_ERR_UNSUPPORTED,
             "gemm_bf16: N=%d exceeds the per-column vectors staged in shared memory", g.N);
-  const int smem_bytes = Cfg::SMEM_BYTES;
   int dev = 0, sms = 0;
   ACX_CUDA(cudaGetDevice(&dev));
   ACX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  const int tiles = ceil_div(g.M, Cfg::BM) * (g.N / BN);
-  const int grid = tiles < sms ? tiles : sms;
-  kern<<<grid, Cfg::THREADS, smem_bytes, st>>>(tmA, tmB, tmOut, g);
-  ACX_CUDA(cudaGetLastError());
+  const int tiles = ceil_div(g.M, Cfg::BM * CG) * (g.N / BN);      // work units: CTAs (CG=1) or CTA pairs (CG=2)
+  const int units = sms / CG;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((tiles < units ? tiles : units) * CG);
+  cfg.blockDim = dim3(Cfg::THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = CG == 2 ? 1 : 0;
+  ACX_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmOut, g));
   return ACX_OK;
 }
 
+// B operand / output maps and tile-shape dispatch.  A CTA pair (CG = 2) is used when there are enough 256-row tiles to
+// fill the 74 pairs; small problems keep one CTA per 128-row tile.
 template <int EPI>
 static int dispatch_bn(const CUtensorMap& tmA, const void* W, const GemmArgs& g, cudaStream_t st) {
-  // tile-N choice: the largest supported BN that divides N (fewer A re-reads, longer MMAs)
   int bn = 0;
-  for (int cand : {256, 192, 128, 96}) {
+  for (int cand : {256, 192, 128, 96}) {   // the largest supported BN that divides N (fewer A re-reads, longer MMAs)
     if (g.N % cand == 0) {
       bn = cand;
       break;
     }
   }
   ACX_CHECK(bn != 0, ACX_ERR_UNSUPPORTED, "gemm_bf16: N=%d is not a multiple of 96/128/192/256", g.N);
+  static const bool pair_ok = getenv("ACX_GEMM_PAIR") == nullptr || atoi(getenv("ACX_GEMM_PAIR")) != 0;
+  const bool pair = pair_ok && (bn == 256 || bn == 192) && (long long)ceil_div(g.M, 256) * (g.N / bn) >= 74;
   CUtensorMap tmB;
-  int rc = make_tmap_2d_bf16(&tmB, W, (uint64_t)g.K, (uint64_t)g.N, (uint64_t)g.K * 2, 64, (uint32_t)bn);
+  int rc = make_tmap_2d_bf16(&tmB, W, (uint64_t)g.K, (uint64_t)g.N, (uint64_t)g.K * 2, 64,
+                             (uint32_t)(pair ? bn / 2 : bn));
   if (rc != ACX_OK) return rc;
   // output: 32-column x 32-row boxes (one per epilogue warp and chunk), 64B swizzle
   CUtensorMap tmOut;
   rc = make_tmap_2d_bf16(&tmOut, g.out, (uint64_t)g.N, (uint64_t)g.M, (uint64_t)g.N * 2, 32, 32,
                          CU_TENSOR_MAP_SWIZZLE_64B);
   if (rc != ACX_OK) return rc;
+  if (pair) {
+    if (bn == 256) return launch_umma_gemm<256, EPI, 8, 2>(tmA, tmB, tmOut, g, st);
+    return launch_umma_gemm<192, EPI, 8, 2>(tmA, tmB, tmOut, g, st);
+  }
   switch (bn) {
-    case 256: return launch_umma_gemm<256, EPI, 8>(tmA, tmB, tmOut, g, st);
-    case 192: return launch_umma_gemm<192, EPI, 8>(tmA, tmB, tmOut, g, st);
-    case 128: return launch_umma_gemm<128, EPI, 8>(tmA, tmB, tmOut, g, st);
-    default:  return launch_umma_gemm<96, EPI, 8>(tmA, tmB, tmOut, g, st);
+    case 256: return launch_umma_gemm<256, EPI, 8, 1>(tmA, tmB, tmOut, g, st);
+    case 192: return launch_umma_gemm<192, EPI, 8, 1>(tmA, tmB, tmOut, g, st);
+    case 128: return launch_umma_gemm<128, EPI, 8, 1>(tmA, tmB, tmOut, g, st);
+    default:  return launch_umma_gemm<96, EPI, 8, 1>(tmA, tmB, tmOut, g, st);
   }
 }
 
