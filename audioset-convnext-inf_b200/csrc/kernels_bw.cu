@@ -22,24 +22,37 @@ __device__ __forceinline__ float load_sample(const int16_t* p) { return __fdiv_r
 template <bool kSplit, typename TIn>
 __global__ void wave_prep_kernel(const TIn* __restrict__ wave, void* __restrict__ hi_, void* __restrict__ lo_,
                                  int L, int pad, int ld_pad) {
+  // 4 consecutive output samples per thread (ld_pad % 8 == 0): 8-byte bf16 / 16-byte fp32 stores
   const int b = blockIdx.y;
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= ld_pad) return;
-  float v = 0.f;
-  if (j < L + 2 * pad) {
-    int s = j - pad;
-    if (s < 0) s = -s;                       // reflect (edge sample not repeated)
-    if (s >= L) s = 2 * (L - 1) - s;
-    v = load_sample(wave + (size_t)b * L + s);
+  const int j0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (j0 >= ld_pad) return;
+  float v[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int j = j0 + i;
+    v[i] = 0.f;
+    if (j < L + 2 * pad) {
+      int s = j - pad;
+      if (s < 0) s = -s;                       // reflect (edge sample not repeated)
+      if (s >= L) s = 2 * (L - 1) - s;
+      v[i] = load_sample(wave + (size_t)b * L + s);
+    }
   }
-  const size_t o = (size_t)b * ld_pad + j;
+  const size_t o = (size_t)b * ld_pad + j0;
   if (kSplit) {
-    bf16 h = __float2bfloat16_rn(v);
-    bf16 l = __float2bfloat16_rn(v - __bfloat162float(h));
-    reinterpret_cast<bf16*>(hi_)[o] = h;
-    reinterpret_cast<bf16*>(lo_)[o] = l;
+    uint32_t h[2], l[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const __nv_bfloat162 hh = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+      const float2 hf = __bfloat1622float2(hh);
+      const __nv_bfloat162 ll = __floats2bfloat162_rn(v[2 * i] - hf.x, v[2 * i + 1] - hf.y);
+      h[i] = *reinterpret_cast<const uint32_t*>(&hh);
+      l[i] = *reinterpret_cast<const uint32_t*>(&ll);
+    }
+    *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(hi_) + o) = make_uint2(h[0], h[1]);
+    *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(lo_) + o) = make_uint2(l[0], l[1]);
   } else {
-    reinterpret_cast<float*>(hi_)[o] = v;
+    *reinterpret_cast<float4*>(reinterpret_cast<float*>(hi_) + o) = make_float4(v[0], v[1], v[2], v[3]);
   }
 }
 
@@ -359,68 +372,99 @@ __global__ void __launch_bounds__(S* C / 2)
 }
 
 // =============================================================================================
-// channels_first LayerNorm + 2x2 patch gather (reference convnext.py:231-234): 16 lanes per INPUT pixel, each lane
-// holds C/32 channel pairs; a half-warp works on NPIX pixels at once so their loads overlap.
+// channels_first LayerNorm + 2x2 patch gather (reference convnext.py:231-234).
+// C/24 lanes per INPUT pixel, 24 channels (three 16-byte vectors in bf16) per lane: every load / store instruction
+// of a warp moves 512 contiguous-per-pixel bytes, statistics are reduced with log2(C/24) shuffles, and each lane
+// works on NPIX pixels at once so their loads overlap.  (First version: 4-byte loads, 28 % of HBM roofline.)
 // =============================================================================================
 template <typename T, int C>
 __global__ void __launch_bounds__(256)
     ln_patchify_kernel(const T* __restrict__ x, const float* __restrict__ ln_w, const float* __restrict__ ln_b,
                        T* __restrict__ a, int B, int H, int W) {
-  using P = Pair<T>;
-  using PT = typename P::type;
-  constexpr int HALF = C / 2;       // pairs per pixel
-  constexpr int PPL = HALF / 16;    // pairs per lane
-  constexpr int NPIX = 4;           // pixels in flight per half-warp
-  const int l16 = threadIdx.x & 15;
+  constexpr int CH = 24;                      // channels per lane
+  constexpr int LPP = C / CH;                 // lanes per pixel: 4 / 8 / 16
+  constexpr int VE = 16 / (int)sizeof(T);     // elements per 16-byte vector
+  constexpr int NV = CH / VE;                 // vectors per lane: 3 (bf16) / 6 (fp32)
+  constexpr int NPIX = 2;                     // pixels in flight per lane group
+  static_assert(C % CH == 0 && (LPP & (LPP - 1)) == 0 && LPP <= 32, "lane split");
+  const int lig = threadIdx.x % LPP;          // lane in group
   const int Ho = H / 2, Wo = W / 2;
   const long long total = (long long)B * Ho * 2 * Wo * 2;
-  const long long hw = (long long)blockIdx.x * (blockDim.x >> 4) + (threadIdx.x >> 4);
-  float2 g[PPL], be[PPL];
+  const long long grp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / LPP;
+  float g[CH], be[CH];
 #pragma unroll
-  for (int j = 0; j < PPL; ++j) {
-    g[j] = *reinterpret_cast<const float2*>(ln_w + 2 * (l16 + 16 * j));
-    be[j] = *reinterpret_cast<const float2*>(ln_b + 2 * (l16 + 16 * j));
+  for (int j = 0; j < CH; j += 4) {
+    *reinterpret_cast<float4*>(&g[j]) = *reinterpret_cast<const float4*>(ln_w + lig * CH + j);
+    *reinterpret_cast<float4*>(&be[j]) = *reinterpret_cast<const float4*>(ln_b + lig * CH + j);
   }
-  float2 v[NPIX][PPL];
+  float v[NPIX][CH];
   size_t dst_off[NPIX];
   bool ok[NPIX];
 #pragma unroll
   for (int q = 0; q < NPIX; ++q) {
-    const long long pix = hw * NPIX + q;
+    const long long pix = grp * NPIX + q;
     ok[q] = pix < total;
     const long long pp = ok[q] ? pix : 0;
     const int wi = (int)(pp % (Wo * 2));
     const int hi = (int)((pp / (Wo * 2)) % (Ho * 2));
     const int b = (int)(pp / ((long long)Wo * 2 * Ho * 2));
-    const PT* src = reinterpret_cast<const PT*>(x) + (((size_t)b * H + hi) * W + wi) * HALF;
+    const T* src = x + (((size_t)b * H + hi) * W + wi) * C + lig * CH;
     const size_t m = ((size_t)b * Ho + (hi >> 1)) * Wo + (wi >> 1);
-    dst_off[q] = m * (size_t)(4 * HALF) + (size_t)((hi & 1) * 2 + (wi & 1)) * HALF;
+    dst_off[q] = m * (size_t)(4 * C) + (size_t)((hi & 1) * 2 + (wi & 1)) * C + lig * CH;
 #pragma unroll
-    for (int j = 0; j < PPL; ++j) v[q][j] = P::unpack(__ldg(src + l16 + 16 * j));
+    for (int j = 0; j < NV; ++j) {
+      const uint4 raw = __ldg(reinterpret_cast<const uint4*>(src) + j);
+      if (sizeof(T) == 2) {
+        float2 f;
+        f = Pair<bf16>::unpack(raw.x); v[q][8 * j + 0] = f.x; v[q][8 * j + 1] = f.y;
+        f = Pair<bf16>::unpack(raw.y); v[q][8 * j + 2] = f.x; v[q][8 * j + 3] = f.y;
+        f = Pair<bf16>::unpack(raw.z); v[q][8 * j + 4] = f.x; v[q][8 * j + 5] = f.y;
+        f = Pair<bf16>::unpack(raw.w); v[q][8 * j + 6] = f.x; v[q][8 * j + 7] = f.y;
+      } else {
+        v[q][4 * j + 0] = __uint_as_float(raw.x);
+        v[q][4 * j + 1] = __uint_as_float(raw.y);
+        v[q][4 * j + 2] = __uint_as_float(raw.z);
+        v[q][4 * j + 3] = __uint_as_float(raw.w);
+      }
+    }
   }
 #pragma unroll
   for (int q = 0; q < NPIX; ++q) {
     float sum = 0.f;
 #pragma unroll
-    for (int j = 0; j < PPL; ++j) sum += v[q][j].x + v[q][j].y;
+    for (int j = 0; j < CH; ++j) sum += v[q][j];
 #pragma unroll
-    for (int o = 8; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    for (int o = LPP / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
     const float mean = sum / C;
     float sq = 0.f;
 #pragma unroll
-    for (int j = 0; j < PPL; ++j) {
-      v[q][j].x -= mean;
-      v[q][j].y -= mean;
-      sq += v[q][j].x * v[q][j].x + v[q][j].y * v[q][j].y;
+    for (int j = 0; j < CH; ++j) {
+      v[q][j] -= mean;
+      sq = fmaf(v[q][j], v[q][j], sq);
     }
 #pragma unroll
-    for (int o = 8; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    for (int o = LPP / 2; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
     const float rstd = 1.0f / sqrtf(sq / C + 1e-6f);
     if (ok[q]) {
-      PT* dst = reinterpret_cast<PT*>(a) + dst_off[q];
+      T* dst = a + dst_off[q];
 #pragma unroll
-      for (int j = 0; j < PPL; ++j)
-        dst[l16 + 16 * j] = P::pack(v[q][j].x * rstd * g[j].x + be[j].x, v[q][j].y * rstd * g[j].y + be[j].y);
+      for (int j = 0; j < NV; ++j) {
+        uint4 o4;
+        if (sizeof(T) == 2) {
+          const int k = 8 * j;
+          o4.x = Pair<bf16>::pack(v[q][k + 0] * rstd * g[k + 0] + be[k + 0], v[q][k + 1] * rstd * g[k + 1] + be[k + 1]);
+          o4.y = Pair<bf16>::pack(v[q][k + 2] * rstd * g[k + 2] + be[k + 2], v[q][k + 3] * rstd * g[k + 3] + be[k + 3]);
+          o4.z = Pair<bf16>::pack(v[q][k + 4] * rstd * g[k + 4] + be[k + 4], v[q][k + 5] * rstd * g[k + 5] + be[k + 5]);
+          o4.w = Pair<bf16>::pack(v[q][k + 6] * rstd * g[k + 6] + be[k + 6], v[q][k + 7] * rstd * g[k + 7] + be[k + 7]);
+        } else {
+          const int k = 4 * j;
+          o4.x = __float_as_uint(v[q][k + 0] * rstd * g[k + 0] + be[k + 0]);
+          o4.y = __float_as_uint(v[q][k + 1] * rstd * g[k + 1] + be[k + 1]);
+          o4.z = __float_as_uint(v[q][k + 2] * rstd * g[k + 2] + be[k + 2]);
+          o4.w = __float_as_uint(v[q][k + 3] * rstd * g[k + 3] + be[k + 3]);
+        }
+        reinterpret_cast<uint4*>(dst)[j] = o4;
+      }
     }
   }
 }
@@ -622,7 +666,7 @@ static int wave_prep_launch(const TIn* wave, void* hi, void* lo, int B, int L, i
             ld_pad);
   ACX_CHECK(B <= 65535, ACX_ERR_ARG, "wave_prep: batch %d exceeds gridDim.y", B);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  dim3 grid(ceil_div(ld_pad, 256), B);
+  dim3 grid(ceil_div(ld_pad, 1024), B);
   if (act_dtype == ACX_BF16) {
     ACX_CHECK(lo != nullptr, ACX_ERR_ARG, "wave_prep: lo buffer required for bf16 split");
     wave_prep_kernel<true, TIn><<<grid, 256, 0, st>>>(wave, hi, lo, L, n_fft / 2, ld_pad);
@@ -698,7 +742,8 @@ int acx_ln_patchify(const void* x, const float* ln_w, const float* ln_b, void* a
   ACX_CHECK((C == 96 || C == 192 || C == 384) && H >= 2 && W >= 2, ACX_ERR_ARG,
             "ln_patchify: unsupported shape C=%d H=%d W=%d (C must be 96, 192 or 384)", C, H, W);
   const long long total = (long long)B * (H / 2) * 2 * (W / 2) * 2;
-  const int blocks = (int)((total + 63) / 64);            // 16 half-warps x 4 pixels per block
+  const long long lanes = (total + 1) / 2 * (C / 24);        // C/24 lanes per pixel, 2 pixels per lane group
+  const int blocks = (int)((lanes + 255) / 256);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
 #define ACX_LNP(TT, CC)                                                                                     \
   ln_patchify_kernel<TT, CC><<<blocks, 256, 0, st>>>(reinterpret_cast<const TT*>(x), ln_w, ln_b,             \

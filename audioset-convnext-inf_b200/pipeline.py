@@ -17,7 +17,10 @@ class HostPipeline:
         self.depth = depth
         self.eng = model._get_engine()
         self.dev = self.eng.device
-        self.copy_stream = torch.cuda.Stream(device=self.dev)
+        # separate copy streams: on ONE stream the D2H of batch i (which waits for its kernels) would sit in front of
+        # the H2D of batch i+1 and serialise the pipeline
+        self.copy_stream = torch.cuda.Stream(device=self.dev)      # host -> device
+        self.d2h_stream = torch.cuda.Stream(device=self.dev)       # device -> host
         self._slots = None
 
     def _alloc(self, batch):
@@ -54,15 +57,15 @@ class HostPipeline:
                 out = self.eng.run(s["raw"], want=self.want)    # int16 PCM is converted inside acx_wave_prep_pcm16
                 s["free"].record(compute)
                 s["done"].record(compute)
-                with torch.cuda.stream(self.copy_stream):
-                    self.copy_stream.wait_event(s["done"])
+                with torch.cuda.stream(self.d2h_stream):
+                    self.d2h_stream.wait_event(s["done"])
                     if s["host"] is None or any(s["host"][k].shape != v.shape for k, v in out.items()):
                         s["host"] = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in out.items()}
                     for k, v in out.items():
                         s["host"][k].copy_(v, non_blocking=True)
                     s["out"] = out                       # keep device tensors alive until the D2H finished
                     s["d2h"] = torch.cuda.Event()
-                    s["d2h"].record(self.copy_stream)
+                    s["d2h"].record(self.d2h_stream)
                 pending.append(s)
             self._drain(pending, results)
         return results

@@ -235,6 +235,19 @@ def main():
         else:
             achieved, peak, unit = work / (avg_ms * 1e-3) / 1e12, peaks["tensor_sust"], "TFLOP/s"
         share = sum(top_ms) / ms_total
+        # every kernel class of the step against its own roof (untimed per-kernel event pass, serialised launches)
+        prof_total = sum(sum(v) for v in by_tag.values())
+        all_kernels = []
+        for tag, v in sorted(by_tag.items(), key=lambda kv: -sum(kv[1])):
+            b, w = eng.algorithmic_work(tag, n_chunk, CLIP_SAMPLES)
+            t = sum(v) / len(v) * 1e-3
+            if w <= 0 or t <= 0:
+                continue
+            ach = w / t / (1e9 if b == "hbm" else 1e12)
+            pk = peaks["hbm"] if b == "hbm" else peaks["tensor_sust"]
+            all_kernels.append({"kernel": tag, "bound": b, "launches": len(v), "avg_launch_ms": round(t * 1e3, 4),
+                                "achieved": round(ach, 1), "unit": "GB/s" if b == "hbm" else "TFLOP/s",
+                                "frac": round(ach / pk, 3), "share_of_step": round(sum(v) / prof_total, 3)})
         res = {
             "metric": "clips/sec (10s@32kHz, bf16)", "value": round(value, 2), "unit": "clips/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_total / args.steps, 4),
@@ -253,7 +266,10 @@ def main():
                          "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peaks["source"] +
                          (" (sustained bf16 figure: kernel timed inside a long step)" if bound == "tensor" else " (copy)"),
                          "launches_timed": len(top_ms), "avg_launch_ms": round(avg_ms, 4),
-                         "share_of_step": round(share, 4)},
+                         "share_of_step": round(share, 4),
+                         "note": "dwconv_ln does 49 fp32 FMA per element on the CUDA cores: its practical roof is the "
+                                 "FP32 pipe (~37% of the HBM figure at 100% FMA issue), see DESIGN.md"},
+            "roofline_all": all_kernels,
         }
         if not args.no_cpu_baseline and world == 1:
             threads = os.cpu_count() or 1
