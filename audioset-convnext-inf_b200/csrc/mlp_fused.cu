@@ -57,14 +57,14 @@ struct MlpCfg {
   static constexpr int D2_COL = 0, D1_COL = 256, TMEM_COLS = 512;
   static constexpr int OUT_CHUNKS = C / 32;           // 32-column output chunks: 3 / 6
   static constexpr int OUT_G0 = (OUT_CHUNKS + 1) / 2;
-  static constexpr int THREADS = 384;
+  static constexpr int THREADS = 512;                 // 4 control + 8 epilogue-1 + 4 epilogue-2 warps
   static_assert(C % 32 == 0 && C <= 192, "D2 must fit 256 TMEM columns");
   static_assert(SLOT % 1024 == 0 && W2_TILE % 1024 == 0, "swizzle alignment");
   static_assert(SMEM_BYTES <= 227 * 1024, "smem budget");
 };
 
 template <int C>
-__global__ void __launch_bounds__(384, 1)
+__global__ void __launch_bounds__(512, 1)
     mlp_fused_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmW1,
                      const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmOut, MlpArgs a) {
   using Cfg = MlpCfg<C>;
@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(384, 1)
       ptx::mbar_init(&h_empty[s], 1);
     }
     ptx::mbar_init(d2_full, 1);
-    ptx::mbar_init(d2_empty, 8);
+    ptx::mbar_init(d2_empty, 4);
     ptx::fence_barrier_init();
   }
   if (warp == 2) {
@@ -244,125 +244,140 @@ __global__ void __launch_bounds__(384, 1)
         ptx::umma_commit(d2_full);
       }
     }
-  } else if (warp >= 4) {
-    // ===================== epilogue warps ====================================================================
+  } else if (warp >= 4 && warp < 12) {
+    // ===================== epilogue-1 warps (8): D1 -> +b1 -> GELU -> bf16 -> swizzled hidden tile ==============
+    // (two 32-column halves per chunk: keeps the live register set under the 128 registers of a 512-thread CTA)
     const int ew = warp - 4;
     const int quad = warp & 3;
     const int group = ew >> 2;
     const int row_in_tile = quad * 32 + lane;
     const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
-    uint8_t* stg = smem + Cfg::OFF_STG + ew * Cfg::STG_PER_WARP;
-    uint8_t* rbuf = stg;                                 // shared with the output staging tile (see below)
-    const int sw64 = (lane >> 1) & 3;
-    const int ld_piece = lane & 3, ld_row = lane >> 2;
-    int it = 0;
     uint32_t gc = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      // ---- epilogue-1: hidden chunks ---------------------------------------------------------------------
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       for (int h = 0; h < Cfg::NC; ++h, ++gc) {
         const int buf = gc & 1;
         const uint32_t par = (gc >> 1) & 1;
-        ptx::mbar_wait_backoff(&d1_full[buf], par);
+        ptx::mbar_wait(&d1_full[buf], par);
         ptx::tc_fence_after();
         const uint32_t t0 = lane_base + Cfg::D1_COL + buf * Cfg::NH + group * 64;
-        uint32_t ra[32], rb[32];
-        ptx::tmem_ld_32x32b_x32(t0, ra);
-        ptx::tmem_ld_32x32b_x32(t0 + 32, rb);
-        ptx::tmem_ld_wait();
-        ptx::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&d1_empty[buf]);          // D1 buffer free for GEMM1(h+2)
         const float* bias = sb1 + h * Cfg::NH + group * 64;
-        uint32_t packed[32];
-        {
-          float2 o[16];
-          bias_gelu_tile<16>(ra, bias, o);
-#pragma unroll
-          for (int j = 0; j < 16; ++j) packed[j] = Pair<bf16>::pack(o[j].x, o[j].y);
-          bias_gelu_tile<16>(rb, bias + 32, o);
-#pragma unroll
-          for (int j = 0; j < 16; ++j) packed[16 + j] = Pair<bf16>::pack(o[j].x, o[j].y);
-        }
-        ptx::mbar_wait(&h_empty[buf], par ^ 1);                   // GEMM2(h-2) finished reading this hidden buffer
         // this warp group's 64 hidden columns are k-block `group` of the hidden tile: one 128 B swizzled row per lane
         uint8_t* hrow = smem + Cfg::OFF_H + (buf * Cfg::KB2 + group) * Cfg::H_TILE + row_in_tile * 128;
+        uint32_t ra[32];
+        ptx::tmem_ld_32x32b_x32(t0, ra);
+        ptx::tmem_ld_wait();
 #pragma unroll
-        for (int q = 0; q < 8; ++q)
-          *reinterpret_cast<uint4*>(hrow + ((q ^ (row_in_tile & 7)) << 4)) =
-              make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
+        for (int half = 0; half < 2; ++half) {
+          uint32_t packed[16];
+          {
+            float2 o[16];
+            bias_gelu_tile<16>(ra, bias + 32 * half, o);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) packed[j] = Pair<bf16>::pack(o[j].x, o[j].y);
+          }
+          if (half == 0) {
+            ptx::tmem_ld_32x32b_x32(t0 + 32, ra);                 // second half's accumulators
+            ptx::mbar_wait(&h_empty[buf], par ^ 1);               // GEMM2(h-2) finished reading this hidden buffer
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            *reinterpret_cast<uint4*>(hrow + (((4 * half + q) ^ (row_in_tile & 7)) << 4)) =
+                make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
+          if (half == 0) {
+            ptx::tmem_ld_wait();
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&d1_empty[buf]);      // D1 buffer free for GEMM1(h+2)
+          }
+        }
         ptx::fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&h_full[buf]);
       }
-      // ---- epilogue-2: output tile -----------------------------------------------------------------------
-      const int m0 = tile * Cfg::BM;
-      const int row0 = m0 + quad * 32;
-      const int ch_begin = group == 0 ? 0 : Cfg::OUT_G0;
-      const int ch_count = group == 0 ? Cfg::OUT_G0 : Cfg::OUT_CHUNKS - Cfg::OUT_G0;
-      uint4 rq[4];
-      auto fetch_resid = [&](int ci) {
-        const int n = (ch_begin + ci) * 32;
+    }
+  } else if (warp >= 12) {
+    // ===================== epilogue-2 warps (4, one per TMEM lane quadrant), off the critical path ==============
+    // D2 -> +b2, *gamma, +residual -> bf16 -> TMA store while the epilogue-1 warps already work on the next tile.
+    // Residual chunks arrive by cp.async (coalesced 16 B pieces, zero-filled beyond M) one chunk ahead, into the same
+    // 2 KB ping-pong tile that then stages the output chunk.
+    constexpr int NCH = C / 32;
+    const int quad = warp & 3;
+    const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+    uint8_t* stg = smem + Cfg::OFF_STG + quad * 4096;
+    const int sw64 = (lane >> 1) & 3;
+    const int ld_piece = lane & 3, ld_row = lane >> 2;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int row0 = tile * Cfg::BM + quad * 32;
+      auto fetch_resid = [&](int c) {
+        uint8_t* dst = stg + (c & 1) * 2048;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          const int r = row0 + ld_row + 8 * q;
-          rq[q] = make_uint4(0u, 0u, 0u, 0u);
-          if (r < a.M) rq[q] = *reinterpret_cast<const uint4*>(a.x + (size_t)r * C + n + ld_piece * 8);
+          const int rr = ld_row + 8 * q;
+          const int r = row0 + rr;
+          const bf16* src = a.x + (size_t)(r < a.M ? r : 0) * C + c * 32 + ld_piece * 8;
+          const uint32_t d = ptx::smem_u32(dst + rr * 64 + ((ld_piece ^ ((rr >> 1) & 3)) << 4));
+          const int nbytes = r < a.M ? 16 : 0;
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(nbytes) : "memory");
         }
+        asm volatile("cp.async.commit_group;" ::: "memory");
       };
+      if (lane == 0) ptx::tma_store_wait_read<0>();              // previous tile's stores have read both tiles
+      __syncwarp();
       fetch_resid(0);
-      ptx::mbar_wait_backoff(d2_full, it & 1);
+      ptx::mbar_wait(d2_full, it & 1);
       ptx::tc_fence_after();
 #pragma unroll
-      for (int ci = 0; ci < Cfg::OUT_G0; ++ci) {
-        if (ci < ch_count) {
-          const int n = (ch_begin + ci) * 32;
-          uint32_t r[32];
-          ptx::tmem_ld_32x32b_x32(lane_base + Cfg::D2_COL + n, r);
-          ptx::tmem_ld_wait();
-          if (ci + 1 == ch_count) {
-            ptx::tc_fence_before();
+      for (int c = 0; c < NCH; ++c) {
+        uint8_t* tbuf = stg + (c & 1) * 2048;
+        uint32_t r[32];
+        ptx::tmem_ld_32x32b_x32(lane_base + Cfg::D2_COL + c * 32, r);
+        if (c + 1 < NCH) {
+          if (c >= 1) {                                          // tile (c+1)&1 was last used by chunk c-1's store
+            if (lane == 0) ptx::tma_store_wait_read<1>();
             __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(d2_empty);
           }
-          // the single staging tile first transposes the coalesced residual fetch (lane <- its own row) ...
-          if (lane == 0) ptx::tma_store_wait_read<0>();          // previous chunk's TMA store has read the tile
+          fetch_resid(c + 1);
+          asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+          asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        ptx::tmem_ld_wait();
+        if (c == NCH - 1) {
+          ptx::tc_fence_before();
           __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(d2_empty);             // D2 free for the next tile's GEMM2
+        }
+        __syncwarp();
+        uint4 res[4];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int rr = ld_row + 8 * q;
-            *reinterpret_cast<uint4*>(rbuf + rr * 64 + ((ld_piece ^ ((rr >> 1) & 3)) << 4)) = rq[q];
-          }
-          __syncwarp();
-          uint4 res[4];
+        for (int j4 = 0; j4 < 4; ++j4) res[j4] = *reinterpret_cast<const uint4*>(tbuf + lane * 64 + ((j4 ^ sw64) << 4));
+        __syncwarp();
+        const int n = c * 32;
 #pragma unroll
-          for (int j4 = 0; j4 < 4; ++j4) res[j4] = *reinterpret_cast<const uint4*>(rbuf + lane * 64 + ((j4 ^ sw64) << 4));
-          __syncwarp();                                          // ... and is then overwritten with the outputs
-          if (ci + 1 < ch_count) fetch_resid(ci + 1);
-#pragma unroll
-          for (int j4 = 0; j4 < 4; ++j4) {
-            const int j = j4 * 8;
-            const float4 bA = *reinterpret_cast<const float4*>(sb2 + n + j);
-            const float4 bB = *reinterpret_cast<const float4*>(sb2 + n + j + 4);
-            const float4 gA = *reinterpret_cast<const float4*>(sgamma + n + j);
-            const float4 gB = *reinterpret_cast<const float4*>(sgamma + n + j + 4);
-            float2 f;
-            uint4 o;
-            f = Pair<bf16>::unpack(res[j4].x);
-            o.x = Pair<bf16>::pack(fmaf(gA.x, __uint_as_float(r[j + 0]) + bA.x, f.x), fmaf(gA.y, __uint_as_float(r[j + 1]) + bA.y, f.y));
-            f = Pair<bf16>::unpack(res[j4].y);
-            o.y = Pair<bf16>::pack(fmaf(gA.z, __uint_as_float(r[j + 2]) + bA.z, f.x), fmaf(gA.w, __uint_as_float(r[j + 3]) + bA.w, f.y));
-            f = Pair<bf16>::unpack(res[j4].z);
-            o.z = Pair<bf16>::pack(fmaf(gB.x, __uint_as_float(r[j + 4]) + bB.x, f.x), fmaf(gB.y, __uint_as_float(r[j + 5]) + bB.y, f.y));
-            f = Pair<bf16>::unpack(res[j4].w);
-            o.w = Pair<bf16>::pack(fmaf(gB.z, __uint_as_float(r[j + 6]) + bB.z, f.x), fmaf(gB.w, __uint_as_float(r[j + 7]) + bB.w, f.y));
-            *reinterpret_cast<uint4*>(stg + lane * 64 + ((j4 ^ sw64) << 4)) = o;
-          }
-          ptx::fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) {
-            ptx::tma_store_2d(&tmOut, stg, n, row0);
-            ptx::tma_store_commit();
-          }
+        for (int j4 = 0; j4 < 4; ++j4) {
+          const int j = j4 * 8;
+          const float4 bA = *reinterpret_cast<const float4*>(sb2 + n + j);
+          const float4 bB = *reinterpret_cast<const float4*>(sb2 + n + j + 4);
+          const float4 gA = *reinterpret_cast<const float4*>(sgamma + n + j);
+          const float4 gB = *reinterpret_cast<const float4*>(sgamma + n + j + 4);
+          float2 f;
+          uint4 o;
+          f = Pair<bf16>::unpack(res[j4].x);
+          o.x = Pair<bf16>::pack(fmaf(gA.x, __uint_as_float(r[j + 0]) + bA.x, f.x), fmaf(gA.y, __uint_as_float(r[j + 1]) + bA.y, f.y));
+          f = Pair<bf16>::unpack(res[j4].y);
+          o.y = Pair<bf16>::pack(fmaf(gA.z, __uint_as_float(r[j + 2]) + bA.z, f.x), fmaf(gA.w, __uint_as_float(r[j + 3]) + bA.w, f.y));
+          f = Pair<bf16>::unpack(res[j4].z);
+          o.z = Pair<bf16>::pack(fmaf(gB.x, __uint_as_float(r[j + 4]) + bB.x, f.x), fmaf(gB.y, __uint_as_float(r[j + 5]) + bB.y, f.y));
+          f = Pair<bf16>::unpack(res[j4].w);
+          o.w = Pair<bf16>::pack(fmaf(gB.z, __uint_as_float(r[j + 6]) + bB.z, f.x), fmaf(gB.w, __uint_as_float(r[j + 7]) + bB.w, f.y));
+          *reinterpret_cast<uint4*>(tbuf + lane * 64 + ((j4 ^ sw64) << 4)) = o;
+        }
+        ptx::fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          ptx::tma_store_2d(&tmOut, tbuf, n, row0);
+          ptx::tma_store_commit();
         }
       }
     }

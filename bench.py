@@ -47,7 +47,7 @@ class ClockSampler:
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                          "-lms", "20", "-i", str(self.index)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -65,14 +65,21 @@ class ClockSampler:
             self.proc.terminate()
             self.t.join(timeout=2)
 
-    def summary(self):
-        ok = [r for r in self.rows if len(r) == 6 and r[0].isdigit()]
+    def mark(self):
+        return len(self.rows)
+
+    def summary(self, lo=0, hi=None):
+        rows = self.rows[lo:hi]
+        where = "timed region"
+        if len([r for r in rows if len(r) == 6 and r[0].isdigit()]) < 2:
+            rows, where = self.rows[lo:], "timed region + e2e region (timed region shorter than two samples)"
+        ok = [r for r in rows if len(r) == 6 and r[0].isdigit()]
         if not ok:
             return None
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in ok)]
         return {"sm_mhz": statistics.median(int(r[0]) for r in ok), "sm_max_mhz": int(ok[0][1]),
-                "reasons": reasons, "samples": len(ok)}
+                "reasons": reasons, "samples": len(ok), "window": where}
 
 
 def build_model(device):
@@ -142,7 +149,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -175,6 +182,8 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(device)
 
+    clocks = ClockSampler(local_rank)
+    clocks.__enter__()                   # started before the warm-up so nvidia-smi is already streaming when timing starts
     for i in range(args.warmup):
         step(i)
     fence()
@@ -190,13 +199,14 @@ def main():
     eng.start_timing(only=top)            # event pairs around the dominant kernel's launches only
     launches0 = eng.launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local_rank) as clocks:
-        fence()
-        e0.record()
-        for i in range(args.steps):
-            step(i)
-        e1.record()
-        fence()
+    fence()
+    mark0 = clocks.mark()
+    e0.record()
+    for i in range(args.steps):
+        step(i)
+    e1.record()
+    fence()
+    mark1 = clocks.mark()
     top_ms = [ms for _, ms in eng.stop_timing()]
     launches = eng.launches - launches0
     ms = torch.tensor([e0.elapsed_time(e1)], device=device)
@@ -224,6 +234,7 @@ def main():
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
     assert len(res) == n_e2e and res[0]["probs"].shape == (BATCH, 527)
     e2e_value = world * BATCH * n_e2e / dt.item()
+    clocks.__exit__()
 
     if rank == 0:
         peaks = _peaks()
@@ -261,7 +272,7 @@ def main():
                     "d2h_bytes_per_step": BATCH * (2 * 527 + 768) * 4, "steps": n_e2e,
                     "api": "HostPipeline(model).run(pinned fp32 host batches) -> host probs/logits; double-buffered H2D/D2H"},
             "gpu_launches": launches,
-            "clocks": clocks.summary(),
+            "clocks": clocks.summary(mark0, mark1),
             "roofline": {"kernel": top, "bound": bound, "achieved": round(achieved, 2), "peak": peak, "unit": unit,
                          "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peaks["source"] +
                          (" (sustained bf16 figure: kernel timed inside a long step)" if bound == "tensor" else " (copy)"),
