@@ -246,6 +246,12 @@ def main():
         else:
             achieved, peak, unit = work / (avg_ms * 1e-3) / 1e12, peaks["tensor_sust"], "TFLOP/s"
         share = sum(top_ms) / ms_total
+        traffic = None            # dram read+write bytes per launch of that kernel, from the committed ncu capture
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.isfile(tpath):
+            tj = json.load(open(tpath))
+            if tj.get("clips_per_launch") == n_chunk:
+                traffic = tj["bytes_per_launch"].get(top)
         # every kernel class of the step against its own roof (untimed per-kernel event pass, serialised launches)
         prof_total = sum(sum(v) for v in by_tag.values())
         all_kernels = []
@@ -274,7 +280,7 @@ def main():
             "gpu_launches": launches,
             "clocks": clocks.summary(mark0, mark1),
             "roofline": {"kernel": top, "bound": bound, "achieved": round(achieved, 2), "peak": peak, "unit": unit,
-                         "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peaks["source"] +
+                         "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peaks["source"] +
                          (" (sustained bf16 figure: kernel timed inside a long step)" if bound == "tensor" else " (copy)"),
                          "launches_timed": len(top_ms), "avg_launch_ms": round(avg_ms, 4),
                          "share_of_step": round(share, 4),
