@@ -228,7 +228,7 @@ template <typename T, int C, int S>
 __global__ void __launch_bounds__(S* C / 2)
     dwconv_ln_kernel(const T* __restrict__ x, const T* __restrict__ w, const float* __restrict__ bias,
                      const float* __restrict__ ln_w, const float* __restrict__ ln_b, T* __restrict__ y, int H,
-                     int W) {
+                     int W, int groups_per_block) {
   using P = Pair<T>;
   using PT = typename P::type;
   constexpr int R = DW_R;
@@ -249,13 +249,37 @@ __global__ void __launch_bounds__(S* C / 2)
   const int grp = cp >> 4;
   const int w0 = (blockIdx.x * S + s) * 7;
   const int b = blockIdx.z;
-  const int h0 = blockIdx.y * R;
   const PT* xp = reinterpret_cast<const PT*>(x) + (size_t)b * H * W * TPS + cp;
   PT* yp = reinterpret_cast<PT*>(y) + (size_t)b * H * W * TPS + cp;
 
-  for (int i = tid; i < 49 * TPS; i += S * TPS) sw[i] = P::unpack(reinterpret_cast<const PT*>(w)[i]);
+  // tap fill: 49 * C / 2 words per block.  Issued 7 loads at a time (the first version's one-load-per-iteration loop
+  // cost ~12 serial L2 round trips per block, a third of a block's lifetime) and amortised over `groups_per_block`
+  // row groups.
+  {
+    constexpr int PER_THREAD = (49 * TPS + S * TPS - 1) / (S * TPS);
+    PT tmp[7];
+#pragma unroll
+    for (int i0 = 0; i0 < PER_THREAD; i0 += 7) {
+#pragma unroll
+      for (int u = 0; u < 7; ++u) {
+        const int i = tid + (i0 + u) * S * TPS;
+        tmp[u] = (i0 + u < PER_THREAD && i < 49 * TPS) ? __ldg(reinterpret_cast<const PT*>(w) + i) : PT{};
+      }
+#pragma unroll
+      for (int u = 0; u < 7; ++u) {
+        const int i = tid + (i0 + u) * S * TPS;
+        if (i0 + u < PER_THREAD && i < 49 * TPS) sw[i] = P::unpack(tmp[u]);
+      }
+    }
+  }
   const float2 bs = make_float2(bias[2 * cp], bias[2 * cp + 1]);
+  const float2 gw = make_float2(ln_w[2 * cp], ln_w[2 * cp + 1]);
+  const float2 gb = make_float2(ln_b[2 * cp], ln_b[2 * cp + 1]);
   __syncthreads();
+
+  for (int grp_i = 0; grp_i < groups_per_block; ++grp_i) {
+  const int h0 = (blockIdx.y * groups_per_block + grp_i) * R;
+  if (h0 >= H) break;   // block-uniform
 
   float2 acc[R][7];
 #pragma unroll
@@ -355,8 +379,6 @@ __global__ void __launch_bounds__(S* C / 2)
       rstd[q] = rsqrtf(var + 1e-6f);
     }
   }
-  const float2 gw = make_float2(ln_w[2 * cp], ln_w[2 * cp + 1]);
-  const float2 gb = make_float2(ln_b[2 * cp], ln_b[2 * cp + 1]);
 #pragma unroll
   for (int r = 0; r < R; ++r) {
     const int h = h0 + r;
@@ -369,6 +391,7 @@ __global__ void __launch_bounds__(S* C / 2)
       orow[(size_t)p * TPS] = P::pack((acc[r][p].x - mean[q]) * sc * gw.x + gb.x, (acc[r][p].y - mean[q]) * sc * gw.y + gb.y);
     }
   }
+  }  // row groups of this block
 }
 
 // =============================================================================================
@@ -623,9 +646,14 @@ static int launch_dwconv(const void* x, const void* w, const float* bias, const 
     ACX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     configured = true;
   }
-  dim3 grid(strips / S, ceil_div(H, DW_R), B);
+  const int row_groups = ceil_div(H, DW_R);
+  // amortise the tap fill where it is large relative to a block's work (C >= 384: 75-150 KB of taps per block);
+  // measured (64 clips): 2 groups per block helps C = 384 / 768 (-10 %), 4 is worse again, and any grouping hurts
+  // C = 96 / 192 (fewer, longer blocks)
+  const int gpb = (C >= 384 && row_groups >= 2) ? 2 : 1;
+  dim3 grid(strips / S, ceil_div(row_groups, gpb), B);
   kern<<<grid, S * C / 2, SMEM, st>>>(reinterpret_cast<const T*>(x), reinterpret_cast<const T*>(w), bias, ln_w, ln_b,
-                                      reinterpret_cast<T*>(y), H, W);
+                                      reinterpret_cast<T*>(y), H, W, gpb);
   ACX_CUDA(cudaGetLastError());
   return ACX_OK;
 }
