@@ -226,7 +226,7 @@ __global__ void __launch_bounds__(GemmCfg<BN, NEPI, CG>::THREADS, 1)
         }
       };
       fetch_resid(0);   // overlaps the wait for the accumulator
-      ptx::mbar_wait_backoff(&tfull_bar[acc], acc_phase);
+      ptx::mbar_wait(&tfull_bar[acc], acc_phase);
       ptx::tc_fence_after();
       const uint32_t t_base = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * Cfg::ACC_STRIDE +
                               ch_begin * Cfg::CHUNK;

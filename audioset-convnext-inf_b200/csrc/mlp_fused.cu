@@ -11,8 +11,9 @@
 //   warp 1   MMA issuer (tcgen05.mma cta_group::1 kind::f16): GEMM1(h) is issued BEFORE GEMM2(h-1) so the tensor pipe
 //            runs while the epilogue warps turn D1(h-1) into the hidden tile
 //   warp 2   TMEM allocator            warp 3   y-tile (A operand) TMA producer
-//   warps 4..11   epilogue-1 (TMEM -> +b1 -> GELU -> bf16 -> swizzled smem) per chunk, epilogue-2
-//            (TMEM -> +b2, *gamma, +residual -> bf16 -> TMA store) per tile
+//   warps 4..11   epilogue-1: D1 (TMEM) -> +b1 -> GELU -> bf16 -> swizzled hidden tile in smem, per chunk
+//   warps 12..15  epilogue-2: D2 (TMEM) -> +b2, *gamma, +residual (cp.async) -> bf16 -> TMA store, per tile, OFF the
+//            critical path (the epilogue-1 warps are already on the next tile)
 // TMEM columns: D2 at 0 (C <= 192 -> 256 reserved), D1[0] at 256, D1[1] at 384.
 #include <stdlib.h>
 
@@ -29,7 +30,6 @@ struct MlpArgs {
   const float* gamma;
   int M;
   unsigned long long* trace;   // optional [16 tiles][2 roles][32 events] SM-clock stamps of CTA 0 (tools/trace_mlp.py)
-  int dbg;   // bring-up / A-B timing switches (ACX_DBG): 1 = skip GELU math, 2 = skip hidden-tile smem store
 };
 
 template <int C_>
@@ -749,7 +749,6 @@ static int launch_mlp96_resident(const void* y, void* x, const void* w1, const f
   a.b2 = b2;
   a.gamma = gamma;
   a.M = M;
-  a.dbg = getenv("ACX_DBG") ? atoi(getenv("ACX_DBG")) : 0;
   a.trace = getenv("ACX_TRACE_PTR") ? reinterpret_cast<unsigned long long*>(strtoull(getenv("ACX_TRACE_PTR"), nullptr, 0)) : nullptr;
   mlp_fused96_kernel<<<tiles < sms ? tiles : sms, 512, Cfg::SMEM_BYTES, st>>>(tmYm, tmYt, tmW1m, tmW1t, tmW2, tmOut, a);
   ACX_CUDA(cudaGetLastError());
@@ -785,7 +784,6 @@ static int launch_mlp(const void* y, void* x, const void* w1, const float* b1, c
   a.b2 = b2;
   a.gamma = gamma;
   a.M = M;
-  a.dbg = 0;
   a.trace = nullptr;
   kern<<<tiles < sms ? tiles : sms, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(tmY, tmW1, tmW2, tmOut, a);
   ACX_CUDA(cudaGetLastError());

@@ -196,3 +196,23 @@ def test_edge_shapes(models, prec):
         m(torch.zeros(1, 2000, device=DEV))                          # too short for the trunk
     with pytest.raises(ValueError):
         m(torch.zeros(320000, device=DEV))                           # not (batch, samples)
+
+
+def test_baseline_config_shapes_front_end_512_and_ragged_200(models, parity_sd):
+    """BASELINE.json configs #3 (front end only, batch 512) and #5 (batch sweep, sizes that are not multiples of the
+    64-clip chunk) at full size: per-clip results must equal the same clip processed alone / in a small batch
+    (clips are independent), and a sample is checked against the oracle."""
+    m = models["bf16"]
+    g = torch.Generator(device=DEV).manual_seed(7)
+    w = (torch.randn(512, 320000, device=DEV, generator=g) * 0.1).clamp_(-1, 1)
+    lm = m.forward_logmel(w)
+    assert lm.shape == (512, 1001, 224) and torch.isfinite(lm).all()
+    idx = [0, 63, 64, 300, 511]
+    small = m.forward_logmel(w[idx].contiguous())
+    assert torch.equal(lm[idx], small)
+    ref = O.frontend(w[idx[:2]].cpu(), parity_sd, torch.float64)
+    assert (lm[idx[:2]].cpu().double() - ref).abs().mean() < 2e-5           # white noise: near-fp32 accuracy
+    out = m(w[:200])                                                         # 64 + 64 + 64 + 8 clips
+    ref_small = m(w[[0, 70, 199]].contiguous())
+    assert torch.equal(out["clipwise_logits"][[0, 70, 199]], ref_small["clipwise_logits"])
+    assert out["clipwise_output"].shape == (200, 527)
