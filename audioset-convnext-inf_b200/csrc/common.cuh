@@ -81,7 +81,9 @@ __device__ __forceinline__ float gelu_erf(float x) {
 // The tile is processed STAGE BY STAGE over all its pairs (packed fp32x2 FADD2/FMUL2/FFMA2 of sm_100): written pair by
 // pair the compiler serialised each pair's 8-deep dependency chain and the epilogue warps ran at ~0.15 IPC (ncu,
 // profiles/r01c); staged, the independent chains interleave.
-template <int NPAIR>
+// kTwice = true returns 2 * gelu (= x + x tanh(.)): the fused MLP folds the missing 0.5 into its layer-scale vector
+// (exact: powers of two), saving one packed multiply per pair in its epilogue-bound inner loop.
+template <int NPAIR, bool kTwice = false>
 __device__ __forceinline__ void bias_gelu_tile(const uint32_t* __restrict__ acc /*[2*NPAIR] fp32 bits*/,
                                                const float* __restrict__ sbias /*smem*/, float2 (&out)[NPAIR]) {
   float2 x[NPAIR], q[NPAIR];
@@ -111,8 +113,12 @@ __device__ __forceinline__ void bias_gelu_tile(const uint32_t* __restrict__ acc 
   }
 #pragma unroll
   for (int i = 0; i < NPAIR; ++i) {
-    const float2 hx = __fmul2_rn(x[i], make_float2(0.5f, 0.5f));
-    out[i] = __ffma2_rn(hx, q[i], hx);
+    if (kTwice) {
+      out[i] = __ffma2_rn(x[i], q[i], x[i]);
+    } else {
+      const float2 hx = __fmul2_rn(x[i], make_float2(0.5f, 0.5f));
+      out[i] = __ffma2_rn(hx, q[i], hx);
+    }
   }
 }
 

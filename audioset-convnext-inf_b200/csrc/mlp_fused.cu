@@ -90,8 +90,9 @@ __global__ void __launch_bounds__(512, 1)
   float* sgamma = sb2 + C;
   for (int i = threadIdx.x; i < Cfg::HD; i += blockDim.x) sb1[i] = a.b1[i];
   for (int i = threadIdx.x; i < C; i += blockDim.x) {
-    sb2[i] = a.b2[i];
-    sgamma[i] = a.gamma[i];
+    // the hidden tile holds 2 * gelu(.), so  x + gamma (0.5 acc + b2) = x + (0.5 gamma) acc + gamma b2:
+    sgamma[i] = 0.5f * a.gamma[i];       // multiplies the GEMM2 accumulator
+    sb2[i] = a.gamma[i] * a.b2[i];       // added together with the residual
   }
 
   if (warp == 0 && ptx::elect_one()) {
@@ -271,7 +272,7 @@ __global__ void __launch_bounds__(512, 1)
           uint32_t packed[16];
           {
             float2 o[16];
-            bias_gelu_tile<16>(ra, bias + 32 * half, o);
+            bias_gelu_tile<16, true>(ra, bias + 32 * half, o);   // 2 * gelu, see sgamma
 #pragma unroll
             for (int j = 0; j < 16; ++j) packed[j] = Pair<bf16>::pack(o[j].x, o[j].y);
           }
@@ -364,13 +365,13 @@ __global__ void __launch_bounds__(512, 1)
           float2 f;
           uint4 o;
           f = Pair<bf16>::unpack(res[j4].x);
-          o.x = Pair<bf16>::pack(fmaf(gA.x, __uint_as_float(r[j + 0]) + bA.x, f.x), fmaf(gA.y, __uint_as_float(r[j + 1]) + bA.y, f.y));
+          o.x = Pair<bf16>::pack(fmaf(gA.x, __uint_as_float(r[j + 0]), bA.x + f.x), fmaf(gA.y, __uint_as_float(r[j + 1]), bA.y + f.y));
           f = Pair<bf16>::unpack(res[j4].y);
-          o.y = Pair<bf16>::pack(fmaf(gA.z, __uint_as_float(r[j + 2]) + bA.z, f.x), fmaf(gA.w, __uint_as_float(r[j + 3]) + bA.w, f.y));
+          o.y = Pair<bf16>::pack(fmaf(gA.z, __uint_as_float(r[j + 2]), bA.z + f.x), fmaf(gA.w, __uint_as_float(r[j + 3]), bA.w + f.y));
           f = Pair<bf16>::unpack(res[j4].z);
-          o.z = Pair<bf16>::pack(fmaf(gB.x, __uint_as_float(r[j + 4]) + bB.x, f.x), fmaf(gB.y, __uint_as_float(r[j + 5]) + bB.y, f.y));
+          o.z = Pair<bf16>::pack(fmaf(gB.x, __uint_as_float(r[j + 4]), bB.x + f.x), fmaf(gB.y, __uint_as_float(r[j + 5]), bB.y + f.y));
           f = Pair<bf16>::unpack(res[j4].w);
-          o.w = Pair<bf16>::pack(fmaf(gB.z, __uint_as_float(r[j + 6]) + bB.z, f.x), fmaf(gB.w, __uint_as_float(r[j + 7]) + bB.w, f.y));
+          o.w = Pair<bf16>::pack(fmaf(gB.z, __uint_as_float(r[j + 6]), bB.z + f.x), fmaf(gB.w, __uint_as_float(r[j + 7]), bB.w + f.y));
           *reinterpret_cast<uint4*>(tbuf + lane * 64 + ((j4 ^ sw64) << 4)) = o;
         }
         ptx::fence_proxy_async_smem();
@@ -449,8 +450,9 @@ __global__ void __launch_bounds__(512, 1)
   float* sgamma = sb2 + C;
   for (int i = threadIdx.x; i < Cfg::HD; i += blockDim.x) sb1[i] = a.b1[i];
   for (int i = threadIdx.x; i < C; i += blockDim.x) {
-    sb2[i] = a.b2[i];
-    sgamma[i] = a.gamma[i];
+    // the hidden tile holds 2 * gelu(.), so  x + gamma (0.5 acc + b2) = x + (0.5 gamma) acc + gamma b2:
+    sgamma[i] = 0.5f * a.gamma[i];       // multiplies the GEMM2 accumulator
+    sb2[i] = a.gamma[i] * a.b2[i];       // added together with the residual
   }
   if (warp == 0 && ptx::elect_one()) {
     ptx::prefetch_tensormap(&tmYm);
@@ -590,7 +592,7 @@ __global__ void __launch_bounds__(512, 1)
           uint32_t packed[16];
           {
             float2 o[16];
-            bias_gelu_tile<16>(ra, bias + 32 * half, o);
+            bias_gelu_tile<16, true>(ra, bias + 32 * half, o);   // 2 * gelu, see sgamma
 #pragma unroll
             for (int j = 0; j < 16; ++j) packed[j] = Pair<bf16>::pack(o[j].x, o[j].y);
           }
@@ -689,13 +691,13 @@ __global__ void __launch_bounds__(512, 1)
           float2 f;
           uint4 o;
           f = Pair<bf16>::unpack(res[j4].x);
-          o.x = Pair<bf16>::pack(fmaf(gA.x, __uint_as_float(r[j + 0]) + bA.x, f.x), fmaf(gA.y, __uint_as_float(r[j + 1]) + bA.y, f.y));
+          o.x = Pair<bf16>::pack(fmaf(gA.x, __uint_as_float(r[j + 0]), bA.x + f.x), fmaf(gA.y, __uint_as_float(r[j + 1]), bA.y + f.y));
           f = Pair<bf16>::unpack(res[j4].y);
-          o.y = Pair<bf16>::pack(fmaf(gA.z, __uint_as_float(r[j + 2]) + bA.z, f.x), fmaf(gA.w, __uint_as_float(r[j + 3]) + bA.w, f.y));
+          o.y = Pair<bf16>::pack(fmaf(gA.z, __uint_as_float(r[j + 2]), bA.z + f.x), fmaf(gA.w, __uint_as_float(r[j + 3]), bA.w + f.y));
           f = Pair<bf16>::unpack(res[j4].z);
-          o.z = Pair<bf16>::pack(fmaf(gB.x, __uint_as_float(r[j + 4]) + bB.x, f.x), fmaf(gB.y, __uint_as_float(r[j + 5]) + bB.y, f.y));
+          o.z = Pair<bf16>::pack(fmaf(gB.x, __uint_as_float(r[j + 4]), bB.x + f.x), fmaf(gB.y, __uint_as_float(r[j + 5]), bB.y + f.y));
           f = Pair<bf16>::unpack(res[j4].w);
-          o.w = Pair<bf16>::pack(fmaf(gB.z, __uint_as_float(r[j + 6]) + bB.z, f.x), fmaf(gB.w, __uint_as_float(r[j + 7]) + bB.w, f.y));
+          o.w = Pair<bf16>::pack(fmaf(gB.z, __uint_as_float(r[j + 6]), bB.z + f.x), fmaf(gB.w, __uint_as_float(r[j + 7]), bB.w + f.y));
           *reinterpret_cast<uint4*>(tbuf + lane * 64 + ((j4 ^ sw64) << 4)) = o;
         }
         ptx::fence_proxy_async_smem();
