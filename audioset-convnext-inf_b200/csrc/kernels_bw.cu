@@ -1,5 +1,5 @@
 // CUDA-core / bandwidth kernels of the hot path (channels-last, H = time, W = mel):
-//   wave_prep        reflect pad + fp32 -> bf16 hi/lo split            (torchlibrosa STFT.forward pad)
+//   wave_prep        reflect pad + fp32 -> scaled fp16 hi/lo split            (torchlibrosa STFT.forward pad)
 //   power_mel_log    re^2+im^2 -> banded mel -> 10 log10 -> bn0        (fp32-accurate path)
 //   stem             4x4/s4 patchify conv + LayerNorm(96)              (CX:688-691, CX:227)
 //   dwconv_ln        depthwise 7x7 + channels-last LayerNorm           (CX:76-78)
@@ -40,17 +40,20 @@ __global__ void wave_prep_kernel(const TIn* __restrict__ wave, void* __restrict_
   }
   const size_t o = (size_t)b * ld_pad + j0;
   if (kSplit) {
+    // fp16 hi / lo of 2^ACX_FE_SCALE_LOG2 * x (see acx.h): 22 mantissa bits for the tensor-core DFT
+    constexpr float kScale = (float)(1 << ACX_FE_SCALE_LOG2);
     uint32_t h[2], l[2];
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
-      const __nv_bfloat162 hh = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-      const float2 hf = __bfloat1622float2(hh);
-      const __nv_bfloat162 ll = __floats2bfloat162_rn(v[2 * i] - hf.x, v[2 * i + 1] - hf.y);
+      const float s0 = v[2 * i] * kScale, s1 = v[2 * i + 1] * kScale;
+      const __half2 hh = __floats2half2_rn(s0, s1);
+      const float2 hf = __half22float2(hh);
+      const __half2 ll = __floats2half2_rn(s0 - hf.x, s1 - hf.y);
       h[i] = *reinterpret_cast<const uint32_t*>(&hh);
       l[i] = *reinterpret_cast<const uint32_t*>(&ll);
     }
-    *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(hi_) + o) = make_uint2(h[0], h[1]);
-    *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(lo_) + o) = make_uint2(l[0], l[1]);
+    *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(hi_) + o) = make_uint2(h[0], h[1]);
+    *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(lo_) + o) = make_uint2(l[0], l[1]);
   } else {
     *reinterpret_cast<float4*>(reinterpret_cast<float*>(hi_) + o) = make_float4(v[0], v[1], v[2], v[3]);
   }

@@ -253,6 +253,10 @@ __device__ __forceinline__ uint64_t umma_desc_sw64_kmajor(uint32_t smem_addr) {
 // Instruction descriptor, kind::f16: A = B = bf16 (K-major), D = fp32, tile M x N.
 //   [4,6) D fmt (1 = f32)  [7,10) A fmt (1 = bf16)  [10,13) B fmt (1 = bf16)
 //   [15] A major (0 = K)   [16] B major (0 = K)     [17,23) N >> 3   [24,29) M >> 4
+// Same with A = B = fp16 (format code 0): 11-bit mantissas, used by the split-precision DFT of the front end.
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int m, int n) {
+  return (1u << 4) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
+}
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) |
          (static_cast<uint32_t>(m >> 4) << 24);

@@ -21,6 +21,7 @@ DEPTHS = (3, 3, 9, 3)
 DIMS = (96, 192, 384, 768)
 N_FFT, HOP, N_MELS, N_BINS, N_CLASSES = 1024, 320, 224, 513, 527
 BN0_EPS = 1e-5
+FE_SCALE_LOG2 = 8          # == ACX_FE_SCALE_LOG2 in include/acx.h
 
 
 def _p(t):
@@ -74,7 +75,7 @@ class PackedWeights:
             re[:m], im[:m] = conv_real[:m], conv_imag[:m]
             dft = torch.stack([re.view(self.n_chunks, 64, N_FFT), im.view(self.n_chunks, 64, N_FFT)], 1)
             dft = dft.reshape(self.n_chunks * 128, N_FFT)
-            self.dft_hi, self.dft_lo = _split_bf16(dft)
+            self.dft_hi, self.dft_lo = _split_f16(dft * float(1 << FE_SCALE_LOG2))
             mw = torch.zeros(nb, 256, **f32)
             mw[:m, :N_MELS] = melW[:m]
             mel = mw.view(self.n_chunks, 64, 256).transpose(1, 2).reshape(self.n_chunks * 256, 64)
@@ -116,6 +117,13 @@ class PackedWeights:
         # ---- head ---------------------------------------------------------------------------
         self.norm_w, self.norm_b = g("norm.weight").contiguous(), g("norm.bias").contiguous()
         self.fc_w, self.fc_b = g("head_audioset.weight").contiguous(), g("head_audioset.bias").contiguous()
+
+
+def _split_f16(x):
+    """fp16 hi + lo (22 mantissa bits) of an already-scaled fp32 tensor (include/acx.h, ACX_FE_SCALE_LOG2)."""
+    hi = x.to(torch.float16)
+    lo = (x - hi.to(torch.float32)).to(torch.float16)
+    return hi.contiguous(), lo.contiguous()
 
 
 def _split_bf16(x):
@@ -170,8 +178,8 @@ class Engine:
         ld_pad = (max(L + N_FFT, HOP * (T + 3)) + 7) // 8 * 8     # fused front end reads whole hops
         ws = dict(T=T, hs=hs, ld_pad=ld_pad)
         if self.frontend == "fused":
-            ws["wav_hi"] = torch.empty(n, ld_pad, device=dev, dtype=torch.bfloat16)
-            ws["wav_lo"] = torch.empty(n, ld_pad, device=dev, dtype=torch.bfloat16)
+            ws["wav_hi"] = torch.empty(n, ld_pad, device=dev, dtype=torch.float16)
+            ws["wav_lo"] = torch.empty(n, ld_pad, device=dev, dtype=torch.float16)
         else:
             ws["wav_pad"] = torch.empty(n, ld_pad, device=dev, dtype=torch.float32)
             ws["spec"] = torch.empty(n * T, 2 * N_BINS, device=dev, dtype=torch.float32)

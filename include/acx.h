@@ -49,10 +49,14 @@ ACX_API int acx_device_ok(void);
 
 /* ---- front end: torchlibrosa Spectrogram + LogmelFilterBank + bn0 (CX:298-306) ------------- */
 
+/* Split-precision operands of the tensor-core DFT are FP16 pairs of the value scaled by 2^ACX_FE_SCALE_LOG2
+ * (hi = fp16(s x), lo = fp16(s x - hi): 22 mantissa bits, lo stays a normal fp16 down to |x| ~ 5e-4). */
+#define ACX_FE_SCALE_LOG2 8
+
 /* Reflect-pad n_fft/2 both sides (torchlibrosa STFT.forward: F.pad(..., mode='reflect')) and
- * split each fp32 sample into bf16 hi + lo (x ~= hi + lo).  wave (B, L) fp32 ->
- * hi, lo (B, ld_pad) bf16 with ld_pad >= L + n_fft, ld_pad % 8 == 0.  If act_dtype == ACX_F32
- * writes one fp32 padded array to `hi` and ignores `lo`. */
+ * split each fp32 sample into the scaled fp16 hi + lo pair above.  wave (B, L) fp32 ->
+ * hi, lo (B, ld_pad) fp16 with ld_pad >= L + n_fft, ld_pad % 8 == 0.  If act_dtype == ACX_F32
+ * writes one fp32 padded (unscaled) array to `hi` and ignores `lo`. */
 ACX_API int acx_wave_prep(const float* wave, void* hi, void* lo, int B, int L, int n_fft, int ld_pad,
                   int act_dtype, void* stream);
 
@@ -69,9 +73,10 @@ ACX_API int acx_power_mel_log(const float* spec, int ld_spec, int n_bins, const 
                       const int32_t* mel_hi, const float* bn_scale, const float* bn_shift, float* out,
                       int rows, int n_mels, void* stream);
 
-/* tensor-core path: one fused kernel, frames x DFT (split-bf16 x3, fp32 accumulate in TMEM) ->
+/* tensor-core path: one fused kernel, frames x DFT (split-fp16 x3, fp32 accumulate in TMEM) ->
  * power -> x mel (split-bf16 x3) -> log10 -> bn0; never writes the spectrogram to HBM.
- * hi/lo: padded split waveform from acx_wave_prep.  dft_hi/lo: (n_chunks*128, n_fft) bf16,
+ * hi/lo: padded split waveform from acx_wave_prep.  dft_hi/lo: (n_chunks*128, n_fft) fp16 pairs of the
+ * 2^ACX_FE_SCALE_LOG2-scaled windowed-DFT rows,
  * chunk c rows [0,64) = real rows of bins [64c, 64c+64), rows [64,128) = imag rows.
  * mel_hi/lo: (n_chunks*256, 64) bf16, chunk c rows m<224 = melW[64c + k, m] (K-major), rest 0.
  * out (B, T, n_mels) fp32. */
