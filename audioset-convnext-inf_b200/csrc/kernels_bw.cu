@@ -349,8 +349,8 @@ __global__ void __launch_bounds__(S* C / 2)
     }
     __syncthreads();
   };
-  float mean[NP], rstd[NP];
   if (kTwoPass) {
+    float mean[NP], rstd[NP];
     float v[NV];
 #pragma unroll
     for (int q = 0; q < NV; ++q) v[q] = q < NP ? acc[q / 7][q % 7].x + acc[q / 7][q % 7].y : 0.f;
@@ -366,32 +366,61 @@ __global__ void __launch_bounds__(S* C / 2)
     block_allreduce(v);   // the first barrier inside also orders the my_tot reads above before its rewrite
 #pragma unroll
     for (int q = 0; q < NP; ++q) rstd[q] = rsqrtf(my_tot[q] * (1.0f / C) + 1e-6f);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int h = h0 + r;
+      if (h >= H) break;
+      PT* orow = yp + ((size_t)h * W + w0) * TPS;
+#pragma unroll
+      for (int p = 0; p < 7; ++p) {
+        const int q = r * 7 + p;
+        const float sc = rstd[q];
+        orow[(size_t)p * TPS] = P::pack((acc[r][p].x - mean[q]) * sc * gw.x + gb.x, (acc[r][p].y - mean[q]) * sc * gw.y + gb.y);
+      }
+    }
   } else {
+    // one pass: sums and sums of squares reduced together; ONE thread per pixel turns them into (rstd, -mean*rstd)
+    // so every other thread only does  out = acc * (rstd*g) + (-mean*rstd*g + b)  with three packed fp32x2 ops
     float v[NV];
 #pragma unroll
     for (int q = 0; q < 32; ++q) {
-      const float ax = q < NP ? acc[q / 7][q % 7].x : 0.f, ay = q < NP ? acc[q / 7][q % 7].y : 0.f;
-      v[q] = ax + ay;
-      v[32 + q] = ax * ax + ay * ay;
+      const float2 a2 = q < NP ? acc[q / 7][q % 7] : make_float2(0.f, 0.f);
+      const float2 sq = __fmul2_rn(a2, a2);
+      v[q] = a2.x + a2.y;
+      v[32 + q] = sq.x + sq.y;
     }
-    block_allreduce(v);
+    halfwarp_reduce_scatter<NV>(v, lane);
+    const int slot = slot_of_lane<NV>(lane & 15);
 #pragma unroll
-    for (int q = 0; q < NP; ++q) {
-      mean[q] = my_tot[q] * (1.0f / C);
-      const float var = fmaxf(my_tot[32 + q] * (1.0f / C) - mean[q] * mean[q], 0.f);
-      rstd[q] = rsqrtf(var + 1e-6f);
+    for (int q = 0; q < PER_LANE; ++q) my_part[slot + q] = v[q];
+    __syncthreads();
+    float2* my_stat = reinterpret_cast<float2*>(my_tot);       // [32] (rstd, -mean * rstd)
+    if (cp < 32) {
+      float su = part[(s * G) * NV + cp], sq = part[(s * G) * NV + 32 + cp];
+#pragma unroll
+      for (int g = 1; g < G; ++g) {                             // fixed order
+        su += part[(s * G + g) * NV + cp];
+        sq += part[(s * G + g) * NV + 32 + cp];
+      }
+      const float mean = su * (1.0f / C);
+      const float var = fmaxf(sq * (1.0f / C) - mean * mean, 0.f);
+      const float rs = rsqrtf(var + 1e-6f);
+      my_stat[cp] = make_float2(rs, -mean * rs);
     }
-  }
+    __syncthreads();
 #pragma unroll
-  for (int r = 0; r < R; ++r) {
-    const int h = h0 + r;
-    if (h >= H) break;
-    PT* orow = yp + ((size_t)h * W + w0) * TPS;
+    for (int r = 0; r < R; ++r) {
+      const int h = h0 + r;
+      if (h >= H) break;
+      PT* orow = yp + ((size_t)h * W + w0) * TPS;
 #pragma unroll
-    for (int p = 0; p < 7; ++p) {
-      const int q = r * 7 + p;
-      const float sc = rstd[q];
-      orow[(size_t)p * TPS] = P::pack((acc[r][p].x - mean[q]) * sc * gw.x + gb.x, (acc[r][p].y - mean[q]) * sc * gw.y + gb.y);
+      for (int p = 0; p < 7; ++p) {
+        const float2 st = my_stat[r * 7 + p];
+        const float2 sc = __fmul2_rn(make_float2(st.x, st.x), gw);
+        const float2 of = __ffma2_rn(make_float2(st.y, st.y), gw, gb);
+        const float2 o = __ffma2_rn(acc[r][p], sc, of);
+        orow[(size_t)p * TPS] = P::pack(o.x, o.y);
+      }
     }
   }
   }  // row groups of this block
