@@ -214,3 +214,21 @@ def test_frontend_fused_logmel(sd, kind, L):
     lim = dict(noise=(1e-5, 3e-4, 3e-5), tones=(1e-4, 2e-3, 1e-3))[kind]
     assert err.max() < 4 * ref_err.max() + 1e-3
     assert err.mean() < lim[0] and err[mask].max() < lim[1] and err.flatten().quantile(0.99) < lim[2]
+
+
+def test_c_abi_rejects_bad_arguments_with_messages():
+    """Error convention of the boundary: non-zero code + thread-local message, nothing launched, no exception in C."""
+    lib = N.load()
+    t = torch.zeros(64, device=DEV)
+    p = t.data_ptr()
+    assert lib.acx_dwconv_ln(p, p, p, p, p, p, 1, 8, 10, 96, N.ACX_BF16, 0) != 0 and "multiple of 7" in N.last_error()
+    assert lib.acx_dwconv_ln(p, p, p, p, p, p, 1, 8, 14, 100, N.ACX_BF16, 0) != 0 and "unsupported channel" in N.last_error()
+    assert lib.acx_dwconv_ln(0, p, p, p, p, p, 1, 8, 14, 96, N.ACX_BF16, 0) != 0 and "null" in N.last_error()
+    assert lib.acx_ln_patchify(p, p, p, p, 1, 8, 14, 100, N.ACX_BF16, 0) != 0 and "unsupported shape" in N.last_error()
+    assert lib.acx_wave_prep(p, p, p, 1, 100, 1024, 2048, N.ACX_BF16, 0) != 0 and "reflect" in N.last_error()
+    assert lib.acx_wave_prep(p, p, p, 1, 2000, 1024, 2000, N.ACX_BF16, 0) != 0 and "ld_pad" in N.last_error()
+    assert lib.acx_frontend_fused(p, p, 4096, p, p, p, p, 7, p, p, p, 1, 1001, 512, 320, 224, 0) != 0
+    assert "n_fft=1024" in N.last_error()
+    assert lib.acx_head(p, p, p, p, p, p, p, p, p, 1, 31, 7, 770, 527, N.ACX_BF16, 0) != 0 and "unsupported" in N.last_error()
+    assert lib.acx_mlp_fused(p, p, p, p, p, p, p, 0, 96, 0) != 0 and "positive" in N.last_error()
+    torch.cuda.synchronize()          # nothing above may have poisoned the context
