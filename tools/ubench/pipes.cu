@@ -1,0 +1,57 @@
+// Micro-benchmark: sustained throughput (lanes / clk / SM) of MUFU.TANH, MUFU.EX2, FFMA, FFMA2 on this GPU.
+// nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o /tmp/pipes tools/ubench/pipes.cu && /tmp/pipes
+#include <cstdio>
+#include <cuda_runtime.h>
+
+template <int OP>
+__global__ void __launch_bounds__(512) k(float* out, int iters, long long* cycles) {
+  float v[8];
+  float2 w[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    v[i] = 0.001f * (threadIdx.x + i);
+    w[i] = make_float2(v[i], v[i] + 1.f);
+  }
+  const float2 c = make_float2(0.999f, 1.001f), d = make_float2(1e-3f, -1e-3f);
+  long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (OP == 0) asm volatile("tanh.approx.f32 %0, %0;" : "+f"(v[i]));
+      if (OP == 1) asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(v[i]));
+      if (OP == 2) asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(v[i]) : "f"(c.x), "f"(d.x));
+      if (OP == 3) w[i] = __ffma2_rn(w[i], c, d);
+      if (OP == 4) { unsigned u = __float_as_uint(v[i]); asm volatile("tanh.approx.f16x2 %0, %0;" : "+r"(u)); v[i] = __uint_as_float(u); }
+    }
+  }
+  long long t1 = clock64();
+  float s = 0;
+  for (int i = 0; i < 8; ++i) s += v[i] + w[i].x + w[i].y;
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+  if (threadIdx.x == 0 && blockIdx.x == 0) *cycles = t1 - t0;
+}
+
+template <int OP>
+void run(const char* name, int per_instr_elems) {
+  float* out;
+  long long* cyc;
+  cudaMalloc(&out, 148 * 512 * sizeof(float));
+  cudaMallocManaged(&cyc, sizeof(long long));
+  const int iters = 4096;
+  k<OP><<<148, 512>>>(out, iters, cyc);
+  cudaDeviceSynchronize();
+  k<OP><<<148, 512>>>(out, iters, cyc);
+  cudaDeviceSynchronize();
+  const double instr_lanes = 512.0 * iters * 8;     // per SM
+  printf("%-22s %8.2f lane-instr/clk/SM  (%6.2f elements/clk/SM)\n", name, instr_lanes / *cyc,
+         instr_lanes * per_instr_elems / *cyc);
+}
+
+int main() {
+  run<0>("tanh.approx.f32", 1);
+  run<4>("tanh.approx.f16x2", 2);
+  run<1>("ex2.approx.ftz.f32", 1);
+  run<2>("fma.rn.f32", 1);
+  run<3>("fma.rn.f32x2 (FFMA2)", 2);
+  return 0;
+}
