@@ -227,8 +227,11 @@ __device__ __forceinline__ int slot_of_lane(int lane) {
   return ((lane & 8) ? NV / 2 : 0) + ((lane & 4) ? NV / 4 : 0) + ((lane & 2) ? NV / 8 : 0) + ((lane & 1) ? NV / 16 : 0);
 }
 
-template <typename T, int C, int S>
-__global__ void __launch_bounds__(S* C / 2)
+// resident blocks the register budget is capped for: 5 x 96, 2 x 192 or 1 x 384 threads (15 / 12 / 12 warps per SM)
+constexpr int dw_min_blocks(int threads) { return threads <= 96 ? 5 : (threads <= 192 ? 2 : 1); }
+
+template <typename T, int C, int S, int PF>
+__global__ void __launch_bounds__(S* C / 2, dw_min_blocks(S* C / 2))
     dwconv_ln_kernel(const T* __restrict__ x, const T* __restrict__ w, const float* __restrict__ bias,
                      const float* __restrict__ ln_w, const float* __restrict__ ln_b, T* __restrict__ y, int H,
                      int W, int groups_per_block) {
@@ -254,6 +257,27 @@ __global__ void __launch_bounds__(S* C / 2)
   const int b = blockIdx.z;
   const PT* xp = reinterpret_cast<const PT*>(x) + (size_t)b * H * W * TPS + cp;
   PT* yp = reinterpret_cast<PT*>(y) + (size_t)b * H * W * TPS + cp;
+
+  // Column halo: only the first / last strip of a row ever leaves the image, so two hoisted predicates replace
+  // the 13 per-element bounds checks; rows outside the image are skipped as a whole (block-uniform).
+  const bool left_ok = w0 > 0, right_ok = w0 + 7 < W;
+  const PT* x0 = xp + ((ptrdiff_t)w0 - 3) * TPS;   // never dereferenced where the predicates are false
+  auto load_row = [&](int ih, PT(&dst)[13]) {
+    const bool row_ok = ih >= 0 && ih < H;
+    const PT* row = x0 + (size_t)(row_ok ? ih : 0) * W * TPS;
+    const bool pl = row_ok && left_ok, pr = row_ok && right_ok;
+#pragma unroll
+    for (int j = 0; j < 13; ++j) {
+      const bool ok = j < 3 ? pl : (j >= 10 ? pr : row_ok);
+      dst[j] = ok ? __ldg(row + j * TPS) : PT{};
+    }
+  };
+  // The first PF input rows are requested BEFORE the tap fill so that their L2/HBM latency overlaps the fill's own
+  // round trip and barrier (ncu: the serial prologue was ~30 % of a block's lifetime).
+  static_assert((R + 6) % PF == 0, "prefetch ring must divide the row count");
+  PT nxt[PF][13];
+#pragma unroll
+  for (int k = 0; k < PF; ++k) load_row((int)blockIdx.y * groups_per_block * R - 3 + k, nxt[k]);
 
   // tap fill: 49 * C / 2 words per block.  Issued 7 loads at a time (the first version's one-load-per-iteration loop
   // cost ~12 serial L2 round trips per block, a third of a block's lifetime) and amortised over `groups_per_block`
@@ -290,30 +314,15 @@ __global__ void __launch_bounds__(S* C / 2)
 #pragma unroll
     for (int p = 0; p < 7; ++p) acc[r][p] = bs;
 
-  // Column halo: only the first / last strip of a row ever leaves the image, so two hoisted predicates replace
-  // the 13 per-element bounds checks; rows outside the image are skipped as a whole (block-uniform).
-  const bool left_ok = w0 > 0, right_ok = w0 + 7 < W;
-  const PT* x0 = xp + ((ptrdiff_t)w0 - 3) * TPS;   // never dereferenced where the predicates are false
-  auto load_row = [&](int ih, PT(&dst)[13]) {
-    const bool row_ok = ih >= 0 && ih < H;
-    const PT* row = x0 + (size_t)(row_ok ? ih : 0) * W * TPS;
-    const bool pl = row_ok && left_ok, pr = row_ok && right_ok;
-#pragma unroll
-    for (int j = 0; j < 13; ++j) {
-      const bool ok = j < 3 ? pl : (j >= 10 ? pr : row_ok);
-      dst[j] = ok ? __ldg(row + j * TPS) : PT{};
-    }
-  };
-
-  PT nxt[13];
-  load_row(h0 - 3, nxt);
   const float2* swc = sw + cp;
 #pragma unroll
   for (int i = 0; i < R + 6; ++i) {
     float2 in[13];
 #pragma unroll
-    for (int j = 0; j < 13; ++j) in[j] = P::unpack(nxt[j]);
-    if (i + 1 < R + 6) load_row(h0 - 3 + i + 1, nxt);          // prefetch the next input row
+    for (int j = 0; j < 13; ++j) in[j] = P::unpack(nxt[i % PF][j]);
+    // prefetch PF rows ahead; past the end of this group, the first rows of the block's next group
+    if (i + PF < R + 6) load_row(h0 - 3 + i + PF, nxt[i % PF]);
+    else if (grp_i + 1 < groups_per_block) load_row(h0 + R - 3 + (i + PF - (R + 6)), nxt[i % PF]);
     const int ih = h0 - 3 + i;
     if (ih >= 0 && ih < H) {                                    // zero padding contributes nothing (block-uniform)
 #pragma unroll
@@ -665,24 +674,27 @@ __global__ void nhwc_to_nchw_kernel(const T* __restrict__ x, float* __restrict__
 }
 
 // ---- launch helpers ---------------------------------------------------------------------------
-template <typename T, int C, int S>
+template <typename T, int C, int S, int PF = 2>
 static int launch_dwconv(const void* x, const void* w, const float* bias, const float* ln_w, const float* ln_b,
                          void* y, int B, int H, int W, cudaStream_t st) {
   const int strips = W / 7;
   ACX_CHECK(strips % S == 0, ACX_ERR_ARG, "dwconv_ln: W/7=%d not a multiple of strips-per-block %d", strips, S);
   constexpr int NV = sizeof(T) == 4 ? 32 : 64;
   constexpr int SMEM = (2 * 49 * (C / 2) + S * (C / 32) * NV + S * NV) * (int)sizeof(float);
-  auto kern = dwconv_ln_kernel<T, C, S>;
+  auto kern = dwconv_ln_kernel<T, C, S, PF>;
   static bool configured = false;
   if (!configured) {
     ACX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     configured = true;
   }
   const int row_groups = ceil_div(H, DW_R);
-  // amortise the tap fill where it is large relative to a block's work (C >= 384: 75-150 KB of taps per block);
-  // measured (64 clips): 2 groups per block helps C = 384 / 768 (-10 %), 4 is worse again, and any grouping hurts
-  // C = 96 / 192 (fewer, longer blocks)
-  const int gpb = (C >= 384 && row_groups >= 2) ? 2 : 1;
+  // Row groups per block.  With the first input rows requested ahead of the tap fill (and the next group's rows
+  // ahead of the LayerNorm phase) one group per block is fastest everywhere except the tiny stage-4 maps, where the
+  // 150 KB tap fill dominates (measured, 64 clips: C=768 0.137 / 0.133 / 0.129 ms at 1 / 2 / 4 groups; C=384
+  // 0.688 / 0.703 / 0.779; C=96 0.783 / 0.807 / 0.829).  ACX_DW_GPB overrides for experiments.
+  static const int gpb_env = [] { const char* e = getenv("ACX_DW_GPB"); return e ? atoi(e) : 0; }();
+  int gpb = (C >= 768 && row_groups >= 4) ? 4 : 1;
+  if (gpb_env > 0) gpb = gpb_env < row_groups ? gpb_env : row_groups;
   dim3 grid(strips / S, ceil_div(row_groups, gpb), B);
   kern<<<grid, S * C / 2, SMEM, st>>>(reinterpret_cast<const T*>(x), reinterpret_cast<const T*>(w), bias, ln_w, ln_b,
                                       reinterpret_cast<T*>(y), H, W, gpb);
@@ -694,23 +706,30 @@ template <typename T>
 static int dispatch_dwconv(const void* x, const void* w, const float* bias, const float* ln_w, const float* ln_b,
                            void* y, int B, int H, int W, int C, cudaStream_t st) {
   const int strips = W / 7;
+  // A/B switches (development only): ACX_DW_PF=1 -> one-row prefetch, ACX_DW_NARROW=1 -> half-width blocks
+  static const bool pf1 = [] { const char* e = getenv("ACX_DW_PF"); return e && e[0] == '1'; }();
+  static const bool narrow = [] { const char* e = getenv("ACX_DW_NARROW"); return e && e[0] == '1'; }();
+#define ACX_DW_LAUNCH(CC, SS) \
+  (pf1 ? launch_dwconv<T, CC, SS, 1>(x, w, bias, ln_w, ln_b, y, B, H, W, st) \
+       : launch_dwconv<T, CC, SS, 2>(x, w, bias, ln_w, ln_b, y, B, H, W, st))
   switch (C) {
     case 96:
-      if (strips % 4 == 0) return launch_dwconv<T, 96, 4>(x, w, bias, ln_w, ln_b, y, B, H, W, st);
-      if (strips % 2 == 0) return launch_dwconv<T, 96, 2>(x, w, bias, ln_w, ln_b, y, B, H, W, st);
+      if (strips % 4 == 0 && !narrow) return ACX_DW_LAUNCH(96, 4);
+      if (strips % 2 == 0) return ACX_DW_LAUNCH(96, 2);
       set_error("dwconv_ln: C=96 needs an even number of 7-pixel strips per row (W=%d)", W);
       return ACX_ERR_UNSUPPORTED;
     case 192:
-      if (strips % 2 == 0) return launch_dwconv<T, 192, 2>(x, w, bias, ln_w, ln_b, y, B, H, W, st);
-      return launch_dwconv<T, 192, 1>(x, w, bias, ln_w, ln_b, y, B, H, W, st);
+      if (strips % 2 == 0 && !narrow) return ACX_DW_LAUNCH(192, 2);
+      return ACX_DW_LAUNCH(192, 1);
     case 384:
-      return launch_dwconv<T, 384, 1>(x, w, bias, ln_w, ln_b, y, B, H, W, st);
+      return ACX_DW_LAUNCH(384, 1);
     case 768:
-      return launch_dwconv<T, 768, 1>(x, w, bias, ln_w, ln_b, y, B, H, W, st);
+      return ACX_DW_LAUNCH(768, 1);
     default:
       set_error("dwconv_ln: unsupported channel count %d (ConvNeXt-Tiny dims are 96/192/384/768)", C);
       return ACX_ERR_UNSUPPORTED;
   }
+#undef ACX_DW_LAUNCH
 }
 
 }  // namespace acx

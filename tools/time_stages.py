@@ -8,12 +8,11 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import audioset_convnext_inf_b200 as acx  # noqa: E402
-from oracle import weights  # noqa: E402
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 prec = sys.argv[2] if len(sys.argv) > 2 else "bf16"
+torch.manual_seed(0)
 m = acx.convnext_tiny(drop_path_rate=0.0, after_stem_dim=[252, 56])
-m.load_state_dict(weights.make_state_dict("init", 0))
 m = m.cuda().eval().set_precision(prec)
 wave = (torch.randn(B, 320000, device="cuda") * 0.1).clamp(-1, 1)
 eng = m._get_engine()
