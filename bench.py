@@ -300,9 +300,10 @@ def main():
         }
         if not args.no_cpu_baseline and world == 1:
             threads = os.cpu_count() or 1
-            v, secs = cpu_reference_clips_per_s(model.state_dict(), clips=4, iters=3, threads=threads)
+            # bounded sample: ~10-15 s of host work (about 240 clips at the ~20 clips/s of a 16-core box)
+            v, secs = cpu_reference_clips_per_s(model.state_dict(), clips=8, iters=30, threads=threads)
             res["cpu_baseline"] = {"value": round(v, 3), "unit": "clips/s", "cores": threads, "kind": "port",
-                                   "sample": f"3 x 4 clips of the 64-clip step ({secs:.1f} s), oracle port of the "
+                                   "sample": f"30 x 8 clips of the 64-clip step ({secs:.1f} s), oracle port of the "
                                              "reference forward, fp32, torch CPU ops"}
         print(json.dumps(res))
     if world > 1:

@@ -31,6 +31,53 @@ __global__ void __launch_bounds__(512) k(float* out, int iters, long long* cycle
   if (threadIdx.x == 0 && blockIdx.x == 0) *cycles = t1 - t0;
 }
 
+// legacy tensor path (HMMA): mma.sync m16n8k16 / m16n8k8, bf16 inputs, fp32 accumulate; 8 independent accumulator
+// fragments per warp.  Reported as warp-level mma instructions / clk / SM.
+template <int K>
+__global__ void __launch_bounds__(512) kmma(float* out, int iters, long long* cycles) {
+  float d[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) d[i][j] = 0.f;
+  unsigned a0 = 0x3f803f80u + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, b0 = 0x3c003c00u, b1 = 0x3c003c01u;
+  long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (K == 16)
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                     : "+f"(d[i][0]), "+f"(d[i][1]), "+f"(d[i][2]), "+f"(d[i][3])
+                     : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+      else
+        asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
+                     : "+f"(d[i][0]), "+f"(d[i][1]), "+f"(d[i][2]), "+f"(d[i][3])
+                     : "r"(a0), "r"(a1), "r"(b0));
+    }
+  }
+  long long t1 = clock64();
+  float s = 0;
+  for (int i = 0; i < 8; ++i) s += d[i][0] + d[i][1] + d[i][2] + d[i][3];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+  if (threadIdx.x == 0 && blockIdx.x == 0) *cycles = t1 - t0;
+}
+
+template <int K>
+void run_mma(const char* name) {
+  float* out;
+  long long* cyc;
+  cudaMalloc(&out, 148 * 512 * sizeof(float));
+  cudaMallocManaged(&cyc, sizeof(long long));
+  const int iters = 4096;
+  kmma<K><<<148, 512>>>(out, iters, cyc);
+  cudaDeviceSynchronize();
+  kmma<K><<<148, 512>>>(out, iters, cyc);
+  cudaDeviceSynchronize();
+  const double warp_instr = 16.0 * iters * 8;       // per SM
+  printf("%-22s %8.3f warp-mma/clk/SM  (%7.1f dense MAC/clk/SM)\n", name, warp_instr / *cyc,
+         warp_instr * 16 * 8 * K / *cyc);
+}
+
 template <int OP>
 void run(const char* name, int per_instr_elems) {
   float* out;
@@ -53,5 +100,7 @@ int main() {
   run<1>("ex2.approx.ftz.f32", 1);
   run<2>("fma.rn.f32", 1);
   run<3>("fma.rn.f32x2 (FFMA2)", 2);
+  run_mma<16>("mma.sync m16n8k16 bf16");
+  run_mma<8>("mma.sync m16n8k8 bf16");
   return 0;
 }
