@@ -123,4 +123,84 @@ __device__ __forceinline__ void bias_gelu_tile(const uint32_t* __restrict__ acc 
   }
 }
 
+// ---- the same GELU split into its three stages for ONE column pair, so that a caller can software-pipeline the
+// MUFU stage (T) of one group of columns against the FMA stages (A, C) of the next.  The fused MLP's epilogue-1 runs
+// 2 warps per scheduler: with whole-tile stages both warps sat in the same stage at the same time and the XU and FMA
+// pipes alternated instead of overlapping (clock trace: ~2.0 k cycles per 128 x 128 chunk against a 1.0 k XU floor).
+struct GeluPair {
+  unsigned long long x, u;   // packed fp32x2
+};
+// Every stage instruction is `asm volatile` in a hand-chosen order: left to itself the compiler re-clusters them into
+// long FMA-only and MUFU-only runs (seen in SASS), which is what the software pipeline is there to avoid.  Because a
+// warp issues in order, the order below keeps dependent instructions >= 4 issue slots apart (four column pairs advance
+// in lock step through the 6-deep polynomial chain) and sprinkles the other group's MUFUs in between.
+__device__ __forceinline__ unsigned long long f2_pack(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void gelu_op_tanh(GeluPair& g) {
+  asm volatile(
+      "{\n\t.reg .f32 lo, hi;\n\tmov.b64 {lo, hi}, %0;\n\ttanh.approx.f32 lo, lo;\n\ttanh.approx.f32 hi, hi;\n\t"
+      "mov.b64 %0, {lo, hi};\n\t}"
+      : "+l"(g.u));
+}
+// stage T on t[0..4) (if kT) interleaved with stage A on a[0..4) (if kA): acc = 8 fp32 accumulator words, sbias_addr =
+// shared-space address of their 8 biases.  (Fetching the biases a whole step ahead into 8 more registers was tried:
+// the kernel sits at the 128-register cap and got 5 % slower.)
+template <bool kT, bool kA>
+__device__ __forceinline__ void gelu_stage_ta4(GeluPair* t, GeluPair* a, const uint32_t* acc, uint32_t sbias_addr) {
+  const unsigned long long k50 = f2_pack(50.0f, 50.0f);
+  const unsigned long long kc = f2_pack(-3.51516788e-04f, -3.51516788e-04f);
+  const unsigned long long kb = f2_pack(3.70056460e-02f, 3.70056460e-02f);
+  const unsigned long long ka = f2_pack(7.97507884e-01f, 7.97507884e-01f);
+  unsigned long long q[4], p[4];
+  if (kT) gelu_op_tanh(t[0]);
+  if (kA) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float2 b;
+      asm("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(b.x), "=f"(b.y) : "r"(sbias_addr + 8 * i));
+      asm volatile("add.rn.f32x2 %0, %1, %2;"
+                   : "=l"(a[i].x)
+                   : "l"(f2_pack(__uint_as_float(acc[2 * i]), __uint_as_float(acc[2 * i + 1]))), "l"(f2_pack(b.x, b.y)));
+    }
+  }
+  if (kT) gelu_op_tanh(t[1]);
+  if (kA) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) asm volatile("mul.rn.f32x2 %0, %1, %1;" : "=l"(q[i]) : "l"(a[i].x));
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      asm volatile(
+          "{\n\t.reg .f32 lo, hi, c;\n\tmov.b64 {lo, hi}, %0;\n\tmov.b64 {c, _}, %1;\n\t"
+          "min.f32 lo, lo, c;\n\tmin.f32 hi, hi, c;\n\tmov.b64 %0, {lo, hi};\n\t}"
+          : "+l"(q[i])
+          : "l"(k50));
+  }
+  if (kT) gelu_op_tanh(t[2]);
+  if (kA) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) asm volatile("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(p[i]) : "l"(q[i]), "l"(kc), "l"(kb));
+  }
+  if (kT) gelu_op_tanh(t[3]);
+  if (kA) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) asm volatile("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(q[i]) : "l"(q[i]), "l"(p[i]), "l"(ka));
+#pragma unroll
+    for (int i = 0; i < 4; ++i) asm volatile("mul.rn.f32x2 %0, %1, %2;" : "=l"(a[i].u) : "l"(a[i].x), "l"(q[i]));
+  }
+}
+// stage C on 8 pairs: 2 * gelu (= x + x tanh(.)) packed to bf16x2; the 8 FMAs first, then the 8 conversions
+__device__ __forceinline__ void gelu_stage_c8_twice_bf16(const GeluPair* g, uint32_t* pk) {
+  unsigned long long o[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) asm volatile("fma.rn.f32x2 %0, %1, %2, %1;" : "=l"(o[i]) : "l"(g[i].x), "l"(g[i].u));
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    asm volatile("{\n\t.reg .f32 lo, hi;\n\tmov.b64 {lo, hi}, %1;\n\tcvt.rn.bf16x2.f32 %0, hi, lo;\n\t}"
+                 : "=r"(pk[i])
+                 : "l"(o[i]));
+}
+
 }  // namespace acx

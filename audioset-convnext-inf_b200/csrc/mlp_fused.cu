@@ -407,7 +407,7 @@ __global__ void __launch_bounds__(512, 1)
   } while (0)
 
 struct Mlp96 {
-  static constexpr int C = 96, HD = 384, BM = 128, NH = 128, NC = 3;
+  static constexpr int C = 96, HD = 384, BM = 128, NH = 64, NC = 6;   // 64-column hidden chunks
   static constexpr int OFF_W1M = 0;                        // 3 x [128 rows x 64 k]  SW128   48 KB
   static constexpr int OFF_W1T = OFF_W1M + 3 * 16384;      // 3 x [128 rows x 32 k]  SW64    24 KB
   static constexpr int OFF_W2 = OFF_W1T + 3 * 8192;        // 6 x [ 96 rows x 64 k]  SW128   72 KB
@@ -418,7 +418,7 @@ struct Mlp96 {
   static constexpr int OFF_BAR = OFF_STG + 8 * 2048;
   static constexpr int OFF_VEC = OFF_BAR + 256;
   static constexpr int SMEM_BYTES = OFF_VEC + (HD + 2 * C) * 4 + 1024;
-  static constexpr int D2_COL = 0, D1_COL = 256, TMEM_COLS = 512;
+  static constexpr int D2_COL = 0, D2_STRIDE = 128, D1_COL = 256, TMEM_COLS = 512;   // D2 x2 | D1 x4 (64 columns each)
   static constexpr int W_BYTES = 3 * 16384 + 3 * 8192 + 6 * 12288;
   static_assert(SMEM_BYTES <= 227 * 1024, "smem budget");
 };
@@ -435,13 +435,13 @@ __global__ void __launch_bounds__(512, 1)
   uint64_t* w_full = bars;            // weights landed (once)
   uint64_t* a_full = bars + 1;
   uint64_t* a_empty = bars + 2;
-  uint64_t* d1_full = bars + 3;       // [2]
-  uint64_t* d1_empty = bars + 5;      // [2]
-  uint64_t* h_full = bars + 7;
-  uint64_t* h_empty = bars + 8;
-  uint64_t* d2_full = bars + 9;
-  uint64_t* d2_empty = bars + 10;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
+  uint64_t* d1_full = bars + 3;       // [4]  GEMM1 accumulators: ring of four 64-column buffers
+  uint64_t* d1_empty = bars + 7;      // [4]
+  uint64_t* h_full = bars + 11;       // [2]  hidden tile: one 128 x 64 buffer per epilogue-1 warp group
+  uint64_t* h_empty = bars + 13;      // [2]
+  uint64_t* d2_full = bars + 15;      // [2]  D2 is double-buffered: epilogue-2 of tile i overlaps GEMM2 of tile i+1
+  uint64_t* d2_empty = bars + 17;     // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -466,14 +466,16 @@ __global__ void __launch_bounds__(512, 1)
     ptx::mbar_init(w_full, 1);
     ptx::mbar_init(a_full, 1);
     ptx::mbar_init(a_empty, 1);
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < 4; ++s) {
       ptx::mbar_init(&d1_full[s], 1);
-      ptx::mbar_init(&d1_empty[s], 8);
+      ptx::mbar_init(&d1_empty[s], 4);
     }
-    ptx::mbar_init(h_full, 8);
-    ptx::mbar_init(h_empty, 1);
-    ptx::mbar_init(d2_full, 1);
-    ptx::mbar_init(d2_empty, 4);
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(&h_full[s], 4);
+      ptx::mbar_init(&h_empty[s], 1);
+      ptx::mbar_init(&d2_full[s], 1);
+      ptx::mbar_init(&d2_empty[s], 4);
+    }
     ptx::fence_barrier_init();
   }
   if (warp == 2) {
@@ -513,59 +515,85 @@ __global__ void __launch_bounds__(512, 1)
     if (ptx::elect_one()) {
       constexpr uint32_t idesc1 = ptx::umma_idesc_bf16(Cfg::BM, Cfg::NH);
       constexpr uint32_t idesc2 = ptx::umma_idesc_bf16(Cfg::BM, C);
-      const uint32_t d2 = tmem_base + Cfg::D2_COL;
       const uint32_t sbase = ptx::smem_u32(smem);
       const uint64_t dAm = ptx::umma_desc_sw128_kmajor(sbase + Cfg::OFF_AM);
       const uint64_t dAt = ptx::umma_desc_sw64_kmajor(sbase + Cfg::OFF_AT);
       ptx::mbar_wait(w_full, 0);
       ptx::tc_fence_after();
-      int it = 0;
-      uint32_t gc = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-        auto gemm2 = [&](int hh, uint32_t gch) {
-          ptx::mbar_wait(h_full, gch & 1);
-          if (hh == 0) ptx::mbar_wait(d2_empty, (it & 1) ^ 1);
+      // FLAT schedule over the CTA's hidden chunks g = 6 * tile_iteration + h (64 hidden columns each):
+      //   G1(0) .. G1(3) | G2(g), G1(g+4) | ...
+      // GEMM1 runs four chunks ahead of GEMM2 through a ring of four TMEM buffers, ACROSS tile boundaries: the two
+      // epilogue-1 warp groups work on chunks g and g+1 at the same time (even / odd chunks), each filling its OWN
+      // hidden-tile buffer, so neither the epilogue nor this thread ever waits for the other within a chunk.  (History,
+      // from clock traces: per-tile order with one 128-column hidden buffer -> epilogue idle 1.5 k of 8.9 k cycles per
+      // tile at tile boundaries and ~0.6 k per chunk waiting for GEMM2 to release the buffer.)
+      const int my_tiles = (int)blockIdx.x < num_tiles ? (num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+      const uint32_t total = (uint32_t)Cfg::NC * my_tiles;
+      auto gemm1 = [&](uint32_t g, int h, int it) {
+        if (h == 0) {
+          ptx::mbar_wait(a_full, it & 1);
           ptx::tc_fence_after();
-#pragma unroll
-          for (int kb = 0; kb < 2; ++kb) {
-            const uint64_t da = ptx::umma_desc_sw128_kmajor(sbase + Cfg::OFF_H + kb * 16384);
-            const uint64_t db = ptx::umma_desc_sw128_kmajor(sbase + Cfg::OFF_W2 + (hh * 2 + kb) * 12288);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) ptx::umma_bf16(d2, da + 2 * k, db + 2 * k, idesc2, (hh | kb | k) != 0 ? 1u : 0u);
-          }
-          ptx::umma_commit(h_empty);
-        };
-        ACX_TRACE(0, 0);
-        ptx::mbar_wait(a_full, it & 1);
-        ptx::tc_fence_after();
-        ACX_TRACE(0, 1);
-        for (int h = 0; h < Cfg::NC; ++h, ++gc) {
-          const int db1 = gc & 1;
-          ptx::mbar_wait(&d1_empty[db1], ((gc >> 1) & 1) ^ 1);
-          ptx::tc_fence_after();
-          ACX_TRACE(0, 2 + 3 * h);
-          const uint32_t d1 = tmem_base + Cfg::D1_COL + db1 * Cfg::NH;
-          const uint64_t dBm = ptx::umma_desc_sw128_kmajor(sbase + Cfg::OFF_W1M + h * 16384);
-          const uint64_t dBt = ptx::umma_desc_sw64_kmajor(sbase + Cfg::OFF_W1T + h * 8192);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) ptx::umma_bf16(d1, dAm + 2 * k, dBm + 2 * k, idesc1, k != 0 ? 1u : 0u);
-#pragma unroll
-          for (int k = 0; k < 2; ++k) ptx::umma_bf16(d1, dAt + 2 * k, dBt + 2 * k, idesc1, 1u);
-          ptx::umma_commit(&d1_full[db1]);
-          ACX_TRACE(0, 3 + 3 * h);
-          if (h == Cfg::NC - 1) ptx::umma_commit(a_empty);
-          if (h >= 1) gemm2(h - 1, gc - 1);
-          ACX_TRACE(0, 4 + 3 * h);
         }
-        gemm2(Cfg::NC - 1, gc - 1);
-        ptx::umma_commit(d2_full);
-        ACX_TRACE(0, 11);
+        const int db1 = g & 3;
+        ptx::mbar_wait(&d1_empty[db1], ((g >> 2) & 1) ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t d1 = tmem_base + Cfg::D1_COL + db1 * Cfg::NH;
+        // W1 rows [64 h, 64 h + 64): second half of a 128-row tile starts 64 rows = 8 swizzle atoms further
+        const uint64_t dBm = ptx::umma_desc_sw128_kmajor(sbase + Cfg::OFF_W1M + (h >> 1) * 16384 + (h & 1) * 8192);
+        const uint64_t dBt = ptx::umma_desc_sw64_kmajor(sbase + Cfg::OFF_W1T + (h >> 1) * 8192 + (h & 1) * 4096);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) ptx::umma_bf16(d1, dAm + 2 * k, dBm + 2 * k, idesc1, k != 0 ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < 2; ++k) ptx::umma_bf16(d1, dAt + 2 * k, dBt + 2 * k, idesc1, 1u);
+        ptx::umma_commit(&d1_full[db1]);
+        if (h == Cfg::NC - 1) ptx::umma_commit(a_empty);          // y tile consumed: the producer may load the next
+      };
+      auto gemm2 = [&](uint32_t g, int h, int it) {
+        const int hb = g & 1;
+        ptx::mbar_wait(&h_full[hb], (g >> 1) & 1);
+        ACX_TRACE(0, 2 * h);
+        if (h == 0) ptx::mbar_wait(&d2_empty[it & 1], ((it >> 1) & 1) ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t d2 = tmem_base + Cfg::D2_COL + (it & 1) * Cfg::D2_STRIDE;
+        const uint64_t da = ptx::umma_desc_sw128_kmajor(sbase + Cfg::OFF_H + hb * 16384);
+        const uint64_t db = ptx::umma_desc_sw128_kmajor(sbase + Cfg::OFF_W2 + h * 12288);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) ptx::umma_bf16(d2, da + 2 * k, db + 2 * k, idesc2, (h | k) != 0 ? 1u : 0u);
+        ptx::umma_commit(&h_empty[hb]);
+        if (h == Cfg::NC - 1) ptx::umma_commit(&d2_full[it & 1]);
+        ACX_TRACE(0, 2 * h + 1);
+      };
+      // GEMM1 look-ahead = ring depth: chunk g+4 reuses chunk g's buffer, which the epilogue released half-way
+      // through chunk g, i.e. before the h_full(g) that gemm2(g) has just waited for
+      constexpr int LA = 4;
+      int h1 = 0, it1 = 0;                     // chunk / tile iteration of the next GEMM1
+      uint32_t g1 = 0;
+      auto issue_gemm1 = [&]() {
+        if (g1 < total) {
+          gemm1(g1, h1, it1);
+          ++g1;
+          if (++h1 == Cfg::NC) {
+            h1 = 0;
+            ++it1;
+          }
+        }
+      };
+      for (int i = 0; i < LA; ++i) issue_gemm1();
+      int h = 0, it = 0;
+      for (uint32_t g = 0; g < total; ++g) {
+        gemm2(g, h, it);        // first: the epilogue group that filled this hidden buffer waits for its release
+        issue_gemm1();          // then top up the GEMM1 ring (four chunks ahead, never urgent)
+        if (++h == Cfg::NC) {
+          h = 0;
+          ++it;
+        }
       }
     }
   } else if (warp >= 4 && warp < 12) {
-    // ===================== epilogue-1 warps (8): D1 -> +b1 -> GELU -> bf16 -> swizzled hidden tile ==============
-    // Each warp owns 32 rows x 64 hidden columns of the chunk, processed as two 32-column halves so that the live
-    // register set stays under the 128 registers a 512-thread CTA allows.
+    // ===================== epilogue-1 warps (2 groups x 4): D1 -> +b1 -> GELU -> bf16 -> swizzled hidden tile =====
+    // Group 0 (warps 4-7) takes the even 64-column chunks, group 1 (warps 8-11) the odd ones; a warp owns 32 rows x
+    // 64 hidden columns of its chunk.  The two warps that share a scheduler therefore sit in different chunks, out of
+    // phase, and each group writes its own 16 KB hidden buffer.
     const int ew = warp - 4;
     const int quad = warp & 3;
     const int group = ew >> 2;
@@ -573,49 +601,64 @@ __global__ void __launch_bounds__(512, 1)
     const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
     const bool tr = (warp == 4 && lane == 0);
     int it = 0;
-    uint32_t gc = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      for (int h = 0; h < Cfg::NC; ++h, ++gc) {
-        const int buf = gc & 1;
-        if (tr) ACX_TRACE(1, 4 * h);
-        ptx::mbar_wait(&d1_full[buf], (gc >> 1) & 1);
+      for (int hc = 0; hc < Cfg::NC / 2; ++hc) {
+        const int h = 2 * hc + group;
+        const uint32_t gc = (uint32_t)Cfg::NC * it + h;
+        const int buf = gc & 3;
+        if (tr) ACX_TRACE(1, 4 * hc);
+        ptx::mbar_wait(&d1_full[buf], (gc >> 2) & 1);
         ptx::tc_fence_after();
-        if (tr) ACX_TRACE(1, 4 * h + 1);
-        const uint32_t t0 = lane_base + Cfg::D1_COL + buf * Cfg::NH + group * 64;
-        const float* bias = sb1 + h * Cfg::NH + group * 64;
-        uint8_t* hrow = smem + Cfg::OFF_H + group * 16384 + row_in_tile * 128;
-        uint32_t ra[32];
-        ptx::tmem_ld_32x32b_x32(t0, ra);
-        ptx::tmem_ld_wait();
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          uint32_t packed[16];
-          {
-            float2 o[16];
-            bias_gelu_tile<16, true>(ra, bias + 32 * half, o);   // 2 * gelu, see sgamma
-#pragma unroll
-            for (int j = 0; j < 16; ++j) packed[j] = Pair<bf16>::pack(o[j].x, o[j].y);
-          }
-          if (half == 0) {
-            ptx::tmem_ld_32x32b_x32(t0 + 32, ra);                 // second half's accumulators
-            ptx::mbar_wait(h_empty, (gc & 1) ^ 1);                // GEMM2 of the previous chunk has read the hidden tile
-          }
-#pragma unroll
-          for (int q = 0; q < 4; ++q)
-            *reinterpret_cast<uint4*>(hrow + (((4 * half + q) ^ (row_in_tile & 7)) << 4)) =
-                make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
-          if (half == 0) {
-            ptx::tmem_ld_wait();
-            ptx::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(&d1_empty[buf]);      // D1 buffer free for GEMM1(h+2)
-            if (tr) ACX_TRACE(1, 4 * h + 2);
-          }
-        }
+        if (tr) ACX_TRACE(1, 4 * hc + 1);
+        const uint32_t t0 = lane_base + Cfg::D1_COL + buf * Cfg::NH;
+        const uint32_t bias = ptx::smem_u32(sb1 + h * Cfg::NH);
+        const uint32_t hrow = ptx::smem_u32(smem + Cfg::OFF_H + group * 16384 + row_in_tile * 128);
+        // Four 16-column quarters, software-pipelined:  A(0) | T(0)+A(1) | C(0) | T(1)+A(2) | C(1) | T(2)+A(3) | ...
+        // (A = bias, polynomial: FMA pipe; T = 2 x MUFU.TANH per pair: XU pipe; C = x + x t, pack, store: FMA pipe).
+        uint32_t raA[16], raB[16];
+        GeluPair gA[8], gB[8];
+        uint32_t pk[8] = {};
+        auto store_quarter = [&](int qi) {
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(hrow + (((2 * qi) ^ (row_in_tile & 7)) << 4)),
+                       "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3])
+                       : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(hrow + (((2 * qi + 1) ^ (row_in_tile & 7)) << 4)),
+                       "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7])
+                       : "memory");
+        };
+        ptx::tmem_ld_32x32b_x16(t0, raA);
+        ptx::tmem_ld_32x32b_x16(t0 + 16, raB);
+        ptx::tmem_ld_wait_dep(raA, raB);
+        gelu_stage_ta4<false, true>(nullptr, gA, raA, bias);                       // A(0)
+        gelu_stage_ta4<false, true>(nullptr, gA + 4, raA + 8, bias + 32);
+        ptx::tmem_ld_32x32b_x16(t0 + 32, raA);
+        gelu_stage_ta4<true, true>(gA, gB, raB, bias + 64);                        // T(0) + A(1)
+        gelu_stage_ta4<true, true>(gA + 4, gB + 4, raB + 8, bias + 96);
+        ptx::tmem_ld_32x32b_x16(t0 + 48, raB);
+        gelu_stage_c8_twice_bf16(gA, pk);                                          // C(0)
+        ptx::mbar_wait(&h_empty[group], ((gc >> 1) & 1) ^ 1);     // GEMM2 of this group's previous chunk has read the buffer
+        store_quarter(0);
+        ptx::tmem_ld_wait_dep(raA, raB);
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&d1_empty[buf]);          // all of this warp's D1 reads landed: free for GEMM1(g+4)
+        if (tr) ACX_TRACE(1, 4 * hc + 2);
+        gelu_stage_ta4<true, true>(gB, gA, raA, bias + 128);                       // T(1) + A(2)
+        gelu_stage_ta4<true, true>(gB + 4, gA + 4, raA + 8, bias + 160);
+        gelu_stage_c8_twice_bf16(gB, pk);                                          // C(1)
+        store_quarter(1);
+        gelu_stage_ta4<true, true>(gA, gB, raB, bias + 192);                       // T(2) + A(3)
+        gelu_stage_ta4<true, true>(gA + 4, gB + 4, raB + 8, bias + 224);
+        gelu_stage_c8_twice_bf16(gA, pk);                                          // C(2)
+        store_quarter(2);
+        gelu_stage_ta4<true, false>(gB, nullptr, nullptr, 0);                      // T(3)
+        gelu_stage_ta4<true, false>(gB + 4, nullptr, nullptr, 0);
+        gelu_stage_c8_twice_bf16(gB, pk);                                          // C(3)
+        store_quarter(3);
         ptx::fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(h_full);
-        if (tr) ACX_TRACE(1, 4 * h + 3);
+        if (lane == 0) ptx::mbar_arrive(&h_full[group]);
+        if (tr) ACX_TRACE(1, 4 * hc + 3);
       }
     }
   } else if (warp >= 12) {
@@ -651,13 +694,13 @@ __global__ void __launch_bounds__(512, 1)
       __syncwarp();
       fetch_resid(0);
       if (tr) ACX_TRACE(1, 12);
-      ptx::mbar_wait(d2_full, it & 1);
+      ptx::mbar_wait(&d2_full[it & 1], (it >> 1) & 1);
       ptx::tc_fence_after();
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
         uint8_t* tbuf = stg + (c & 1) * 2048;
         uint32_t r[32];
-        ptx::tmem_ld_32x32b_x32(lane_base + Cfg::D2_COL + c * 32, r);
+        ptx::tmem_ld_32x32b_x32(lane_base + Cfg::D2_COL + (it & 1) * Cfg::D2_STRIDE + c * 32, r);
         if (c + 1 < 3) {
           if (c >= 1) {                                          // tile (c+1)&1 was last used by chunk c-1's store
             if (lane == 0) ptx::tma_store_wait_read<1>();
@@ -672,7 +715,7 @@ __global__ void __launch_bounds__(512, 1)
         if (c == 2) {
           ptx::tc_fence_before();
           __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(d2_empty);             // D2 free for the next tile's GEMM2
+          if (lane == 0) ptx::mbar_arrive(&d2_empty[it & 1]);   // this D2 buffer is free for tile i+2's GEMM2
           if (tr) ACX_TRACE(1, 13);
         }
         __syncwarp();

@@ -1,5 +1,5 @@
 """Bring-up aid: SM-clock timeline of CTA 0 of the weight-resident fused MLP kernel (first 16 tiles).
-role 0 = MMA thread, role 1 = epilogue warp 4.  usage: python tools/trace_mlp.py"""
+role 0 = MMA thread, role 1 = epilogue-1 warp 4 (group 0: even chunks) and epilogue-2 warp 12.  usage: python tools/trace_mlp.py"""
 import os
 import sys
 
@@ -28,12 +28,9 @@ N.call("acx_mlp_fused", y.data_ptr(), x.data_ptr(), w1.data_ptr(), b1.data_ptr()
 torch.cuda.synchronize()
 t = trace.cpu().view(16, 2, 32)
 t0 = int(t[t > 0].min())
-names0 = ["tile start", "a_full", "d1e(0)", "g1(0) issued", "g2(-) issued", "d1e(1)", "g1(1) issued", "g2(0) issued", "d1e(2)",
-          "g1(2) issued", "g2(1) issued", "g2(2)+d2_full issued"]
-names1 = ["E1(0) start", "d1_full(0)", "ld done(0)", "h_full(0)", "E1(1) start", "d1_full(1)", "ld done(1)", "h_full(1)",
-          "E1(2) start", "d1_full(2)", "ld done(2)", "h_full(2)", "d2_full", "E2 ld0", "E2 ld1", "tile end",
-          "E2c0 store_wait", "E2c0 rq->smem", "E2c0 res<-smem+fetch", "E2c0 math+sts", "E2c0 fence", "E2c0 tma issued",
-          "E1(0) math done", "E1(0) h_empty ok", "E1(0) sts done"]
+names0 = [f"g2({h}) {w}" for h in range(6) for w in ("h_full seen", "issued")]
+names1 = [f"E1({2 * hc}) {w}" for hc in range(3) for w in ("start", "d1_full", "d1 released", "h_full")]
+names1 += ["E2 resid requested", "E2 D2 released", "-", "tile end"] + ["-"] * 9
 for it in range(4, 6):
     print(f"--- tile iteration {it} (cycles since first stamp)")
     ev = [(int(t[it, 0, i]) - t0, "MMA " + names0[i]) for i in range(12) if t[it, 0, i] > 0]

@@ -21,6 +21,14 @@ __global__ void __launch_bounds__(512) k(float* out, int iters, long long* cycle
       if (OP == 1) asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(v[i]));
       if (OP == 2) asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(v[i]) : "f"(c.x), "f"(d.x));
       if (OP == 3) w[i] = __ffma2_rn(w[i], c, d);
+      if (OP == 5 || OP == 6) {   // mixed: 1 MUFU.TANH + 3 (OP 5) or 1 (OP 6) FFMA2 per slot, independent chains
+        asm volatile("tanh.approx.f32 %0, %0;" : "+f"(v[i]));
+        w[i] = __ffma2_rn(w[i], c, d);
+        if (OP == 5) {
+          w[(i + 3) & 7] = __ffma2_rn(w[(i + 3) & 7], c, d);
+          w[(i + 5) & 7] = __ffma2_rn(w[(i + 5) & 7], c, d);
+        }
+      }
       if (OP == 4) { unsigned u = __float_as_uint(v[i]); asm volatile("tanh.approx.f16x2 %0, %0;" : "+r"(u)); v[i] = __uint_as_float(u); }
     }
   }
@@ -100,6 +108,8 @@ int main() {
   run<1>("ex2.approx.ftz.f32", 1);
   run<2>("fma.rn.f32", 1);
   run<3>("fma.rn.f32x2 (FFMA2)", 2);
+  run<5>("mix 1 tanh + 3 FFMA2", 1);   // lane-instr counts the tanh only: 16 = XU-bound, less = pipes do not overlap
+  run<6>("mix 1 tanh + 1 FFMA2", 1);
   run_mma<16>("mma.sync m16n8k16 bf16");
   run_mma<8>("mma.sync m16n8k8 bf16");
   return 0;
