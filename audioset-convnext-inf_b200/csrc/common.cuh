@@ -79,54 +79,15 @@ __device__ __forceinline__ float gelu_erf(float x) {
 // reference uses (nn.GELU(), convnext.py:65): max |err| 2.6e-5 over all x (textbook tanh-GELU: 4.7e-4), ~10x below the
 // bf16 rounding applied to the result; x^2 is clamped at 50 (tanh saturated) so the negative x^4 term cannot flip the
 // sign for |x| > 11.  Checked on the CPU by tests/test_host_logic.py::test_gelu_fit_against_exact_erf.
-// The tile is processed STAGE BY STAGE over all its pairs (packed fp32x2 FADD2/FMUL2/FFMA2 of sm_100): written pair by
-// pair the compiler serialised each pair's 8-deep dependency chain and the epilogue warps ran at ~0.15 IPC (ncu,
-// profiles/r01c); staged, the independent chains interleave.
-// kTwice = true returns 2 * gelu (= x + x tanh(.)): the fused MLP folds the missing 0.5 into its layer-scale vector
-// (exact: powers of two), saving one packed multiply per pair in its epilogue-bound inner loop.
-template <int NPAIR, bool kTwice = false>
-__device__ __forceinline__ void bias_gelu_tile(const uint32_t* __restrict__ acc /*[2*NPAIR] fp32 bits*/,
-                                               const float* __restrict__ sbias /*smem*/, float2 (&out)[NPAIR]) {
-  float2 x[NPAIR], q[NPAIR];
-#pragma unroll
-  for (int i = 0; i < NPAIR; ++i)
-    x[i] = __fadd2_rn(make_float2(__uint_as_float(acc[2 * i]), __uint_as_float(acc[2 * i + 1])),
-                      *reinterpret_cast<const float2*>(sbias + 2 * i));
-#pragma unroll
-  for (int i = 0; i < NPAIR; ++i) q[i] = __fmul2_rn(x[i], x[i]);
-#pragma unroll
-  for (int i = 0; i < NPAIR; ++i) {
-    q[i].x = fminf(q[i].x, 50.0f);
-    q[i].y = fminf(q[i].y, 50.0f);
-  }
-#pragma unroll
-  for (int i = 0; i < NPAIR; ++i) {
-    const float2 p = __ffma2_rn(q[i], make_float2(-3.51516788e-04f, -3.51516788e-04f),
-                                make_float2(3.70056460e-02f, 3.70056460e-02f));
-    q[i] = __ffma2_rn(q[i], p, make_float2(7.97507884e-01f, 7.97507884e-01f));
-  }
-#pragma unroll
-  for (int i = 0; i < NPAIR; ++i) q[i] = __fmul2_rn(x[i], q[i]);
-#pragma unroll
-  for (int i = 0; i < NPAIR; ++i) {
-    asm("tanh.approx.f32 %0, %1;" : "=f"(q[i].x) : "f"(q[i].x));
-    asm("tanh.approx.f32 %0, %1;" : "=f"(q[i].y) : "f"(q[i].y));
-  }
-#pragma unroll
-  for (int i = 0; i < NPAIR; ++i) {
-    if (kTwice) {
-      out[i] = __ffma2_rn(x[i], q[i], x[i]);
-    } else {
-      const float2 hx = __fmul2_rn(x[i], make_float2(0.5f, 0.5f));
-      out[i] = __ffma2_rn(hx, q[i], hx);
-    }
-  }
-}
-
-// ---- the same GELU split into its three stages for ONE column pair, so that a caller can software-pipeline the
-// MUFU stage (T) of one group of columns against the FMA stages (A, C) of the next.  The fused MLP's epilogue-1 runs
-// 2 warps per scheduler: with whole-tile stages both warps sat in the same stage at the same time and the XU and FMA
-// pipes alternated instead of overlapping (clock trace: ~2.0 k cycles per 128 x 128 chunk against a 1.0 k XU floor).
+// All arithmetic is packed fp32x2 (FADD2 / FMUL2 / FFMA2 of sm_100).  The "twice" form returns 2 * gelu
+// (= x + x tanh(.)): the fused MLP folds the missing 0.5 into its layer-scale vector (exact: powers of two).
+//
+// The GELU is split into three stages for a column pair -- A: bias + polynomial (FMA pipe), T: 2 x MUFU.TANH (XU
+// pipe), C: x + x t (FMA pipe) -- so that callers can software-pipeline T of one group of columns against A of the
+// next.  History (clock traces + ncu, profiles/): written pair by pair the compiler serialised each pair's 8-deep chain
+// (~0.15 IPC per epilogue warp); written stage by stage over a whole tile, the two epilogue warps that share a
+// scheduler sat in the same stage at the same time and the XU and FMA pipes alternated instead of overlapping
+// (~2.0 k cycles per 128 x 128 chunk against a 1.0 k XU floor).
 struct GeluPair {
   unsigned long long x, u;   // packed fp32x2
 };
@@ -201,6 +162,28 @@ __device__ __forceinline__ void gelu_stage_c8_twice_bf16(const GeluPair* g, uint
     asm volatile("{\n\t.reg .f32 lo, hi;\n\tmov.b64 {lo, hi}, %1;\n\tcvt.rn.bf16x2.f32 %0, hi, lo;\n\t}"
                  : "=r"(pk[i])
                  : "l"(o[i]));
+}
+
+// Drop-in for bias_gelu_tile<16, kTwice> built from the stages above: T of pairs [4k, 4k+4) is interleaved with A of
+// pairs [4k+4, 4k+8), so each warp's instruction stream mixes XU and FMA work instead of alternating long phases.
+template <bool kTwice>
+__device__ __forceinline__ void bias_gelu_tile16_sp(const uint32_t* __restrict__ acc /*[32] fp32 bits*/,
+                                                    const float* __restrict__ sbias /*smem*/, float2 (&out)[16]) {
+  GeluPair g[16];
+  const uint32_t sb = static_cast<uint32_t>(__cvta_generic_to_shared(sbias));
+  gelu_stage_ta4<false, true>(nullptr, g, acc, sb);
+  gelu_stage_ta4<true, true>(g, g + 4, acc + 8, sb + 32);
+  gelu_stage_ta4<true, true>(g + 4, g + 8, acc + 16, sb + 64);
+  gelu_stage_ta4<true, true>(g + 8, g + 12, acc + 24, sb + 96);
+  gelu_stage_ta4<true, false>(g + 12, nullptr, nullptr, 0);
+  const unsigned long long khalf = f2_pack(0.5f, 0.5f);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    unsigned long long o, x = g[i].x;
+    if (!kTwice) asm volatile("mul.rn.f32x2 %0, %1, %2;" : "=l"(x) : "l"(g[i].x), "l"(khalf));
+    asm volatile("fma.rn.f32x2 %0, %1, %2, %1;" : "=l"(o) : "l"(x), "l"(g[i].u));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(out[i].x), "=f"(out[i].y) : "l"(o));
+  }
 }
 
 }  // namespace acx

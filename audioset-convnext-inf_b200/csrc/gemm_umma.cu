@@ -252,7 +252,7 @@ __global__ void __launch_bounds__(GemmCfg<BN, NEPI, CG>::THREADS, 1)
           float v[32];
           if (EPI == ACX_EPI_BIAS_GELU) {
             float2 o[16];
-            bias_gelu_tile<16>(r, sbias + n, o);
+            bias_gelu_tile16_sp<false>(r, sbias + n, o);
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               v[2 * j] = o[j].x;

@@ -272,7 +272,7 @@ __global__ void __launch_bounds__(512, 1)
           uint32_t packed[16];
           {
             float2 o[16];
-            bias_gelu_tile<16, true>(ra, bias + 32 * half, o);   // 2 * gelu, see sgamma
+            bias_gelu_tile16_sp<true>(ra, bias + 32 * half, o);   // 2 * gelu, see sgamma
 #pragma unroll
             for (int j = 0; j < 16; ++j) packed[j] = Pair<bf16>::pack(o[j].x, o[j].y);
           }

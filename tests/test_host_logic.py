@@ -129,7 +129,7 @@ def test_out_time_dims_match_oracle_shapes(L):
 
 
 def test_gelu_fit_against_exact_erf():
-    """The tensor-core epilogue's tanh-form GELU (gemm_umma.cu::gelu_fast) vs nn.GELU()."""
+    """The tensor-core epilogues' tanh-form GELU (csrc/common.cuh: gelu_stage_ta4 coefficients) vs nn.GELU()."""
     x = torch.linspace(-60, 60, 1200001)
     x2 = torch.clamp(x * x, max=50.0)
     inner = x * (7.97507884e-01 + x2 * (3.70056460e-02 + x2 * -3.51516788e-04))
