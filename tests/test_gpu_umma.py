@@ -89,7 +89,10 @@ def test_umma_rejects_bad_arguments():
     assert rc != 0 and "multiple" in N.last_error()
 
 
-@pytest.mark.parametrize("C,M", [(96, 128), (96, 1000), (96, 14112 * 2), (192, 300), (192, 3528 * 2), (96, 128 * 400)])
+# the last three cases give every persistent CTA 6-12 row tiles (ragged tail included), so the D1 ring (4 buffers), the
+# per-group hidden buffers and the double-buffered D2 of mlp_fused96 wrap their mbarrier phases several times
+@pytest.mark.parametrize("C,M", [(96, 128), (96, 1000), (96, 14112 * 2), (192, 300), (192, 3528 * 2), (96, 128 * 400),
+                                 (96, 128 * 148 * 6 + 77), (96, 14112 * 16), (192, 3528 * 16)])
 def test_mlp_fused_matches_reference_block_mlp(C, M):
     """acx_mlp_fused (hidden tile kept in TMEM/SMEM) vs fp64 evaluation of CX:79-86 on the same bf16 operands,
     and vs the two-kernel tcgen05 path (pw1+GELU, pw2+gamma+residual)."""
