@@ -673,6 +673,31 @@ __global__ void nhwc_to_nchw_kernel(const T* __restrict__ x, float* __restrict__
   }
 }
 
+// =============================================================================================
+// polyphase sinc resampler + pad / crop (reference demo_convnext.py:52-67 via torchaudio.functional.resample).
+// Thread per output sample; a warp's lanes share the input window (broadcast loads) and read consecutive phases of
+// the transposed tap table (coalesced).  One clip per demo call: ~150 MFLOP, latency-bound, not a hot kernel.
+// =============================================================================================
+__global__ void __launch_bounds__(256)
+    resample_fit_kernel(const float* __restrict__ x, int ld_in, const float* __restrict__ taps, float* __restrict__ out,
+                        int ld_out, int L_in, int orig, int newf, int width, int n_out, long long target) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_out) return;
+  const float* xb = x + (size_t)blockIdx.y * ld_in;
+  float acc = 0.f;
+  if (i < target) {
+    const int f = i / newf, p = i - f * newf;
+    const long long base = (long long)f * orig - width;
+    const int K = 2 * width + orig;
+    for (int k = 0; k < K; ++k) {
+      const long long idx = base + k;
+      const float v = (idx >= 0 && idx < L_in) ? __ldg(xb + idx) : 0.f;
+      acc = fmaf(__ldg(taps + (size_t)k * newf + p), v, acc);
+    }
+  }
+  out[(size_t)blockIdx.y * ld_out + i] = acc;
+}
+
 // ---- launch helpers ---------------------------------------------------------------------------
 template <typename T, int C, int S, int PF = 2>
 static int launch_dwconv(const void* x, const void* w, const float* bias, const float* ln_w, const float* ln_b,
@@ -866,6 +891,22 @@ int acx_nhwc_to_nchw_f32(const void* x, float* out, int B, int H, int W, int C, 
     nhwc_to_nchw_kernel<bf16><<<grid, block, 0, st>>>(reinterpret_cast<const bf16*>(x), out, HW, C);
   else
     nhwc_to_nchw_kernel<float><<<grid, block, 0, st>>>(reinterpret_cast<const float*>(x), out, HW, C);
+  ACX_CUDA(cudaGetLastError());
+  return ACX_OK;
+}
+
+int acx_resample_fit(const float* x, int ld_in, const float* taps, float* out, int ld_out, int B, int L_in, int orig,
+                     int newf, int width, int n_out, void* stream) {
+  ACX_CHECK(x && taps && out, ACX_ERR_ARG, "resample_fit: null pointer");
+  ACX_CHECK(B > 0 && B <= 65535 && L_in > 0 && n_out > 0, ACX_ERR_ARG, "resample_fit: bad sizes B=%d L_in=%d n_out=%d", B,
+            L_in, n_out);
+  ACX_CHECK(orig > 0 && newf > 0 && width > 0, ACX_ERR_ARG, "resample_fit: bad rates %d -> %d (width %d)", orig, newf,
+            width);
+  ACX_CHECK(ld_in >= L_in && ld_out >= n_out, ACX_ERR_ARG, "resample_fit: row pitch smaller than row length");
+  const long long target = ((long long)newf * L_in + orig - 1) / orig;
+  dim3 grid(ceil_div(n_out, 256), B);
+  resample_fit_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, ld_in, taps, out, ld_out, L_in, orig,
+                                                                                newf, width, n_out, target);
   ACX_CUDA(cudaGetLastError());
   return ACX_OK;
 }

@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Counterpart of the reference's demo_convnext.py (one clip -> tags @0.25, scene and frame embeddings), on the
-B200 path.  Reads the wav with scipy (torchaudio.load needs torchcodec, absent here), pads / crops to 10 s at 32 kHz
-exactly as demo_convnext.py:61-67 does, and runs ONE forward for all three outputs.
+B200 path.  Reads the wav with scipy (torchaudio.load needs torchcodec, absent here); resampling to 32 kHz and the
+pad / crop to 10 s of demo_convnext.py:52-67 are one GPU launch (preprocess.resample_fit), then ONE forward gives all
+three outputs.
 
   python demo.py --checkpoint model.safetensors --wav clip.wav [--labels class_labels_indices.csv] [--precision fp32]
 """
@@ -28,10 +29,7 @@ def read_wav(path):
         wave = data.astype(np.float32) / 32768.0            # torchaudio.load normalisation
     else:
         wave = data.astype(np.float32)
-    if sr != SR:
-        raise SystemExit(f"{path}: {sr} Hz; resample to {SR} Hz first (the reference uses torchaudio resample, "
-                         "demo_convnext.py:53-59, which is out of scope here)")
-    return wave
+    return wave, sr
 
 
 def main():
@@ -46,14 +44,12 @@ def main():
              acx.convnext_tiny(pretrained=False, strict=False, drop_path_rate=0.0, after_stem_dim=[252, 56]))
     print("# params:", sum(p.numel() for p in model.parameters() if p.requires_grad))
     model = model.to("cuda").eval().set_precision(args.precision)
-    wave = read_wav(args.wav)
-    if wave.shape[0] < TARGET:
-        print("Padding waveform")
-        wave = np.pad(wave, (0, TARGET - wave.shape[0]))
-    elif wave.shape[0] > TARGET:
-        print("Cropping waveform")
-        wave = wave[:TARGET]
-    out = model.forward_all(torch.from_numpy(wave)[None].to("cuda"))
+    wave, sr = read_wav(args.wav)
+    if sr != SR:
+        print("Resampling from %d to 32000 Hz" % sr)
+    # resample (identity at 32 kHz) + constant pad / crop to 10 s, on the GPU
+    clip = acx.preprocess.resample_fit(torch.from_numpy(wave)[None].to("cuda"), sr, SR, TARGET)
+    out = model.forward_all(clip)
     probs = out["clipwise_output"][0].cpu().numpy()
     print("logits size:", tuple(out["clipwise_logits"].shape))
     labels = np.where(probs > args.threshold)[0]

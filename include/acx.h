@@ -128,6 +128,16 @@ ACX_API int acx_head(const void* x, const float* ln_w, const float* ln_b, const 
 /* x (B,H,W,C) act_dtype -> out (B,C,H,W) fp32: the layout forward_frame_embeddings returns (CX:399-402). */
 ACX_API int acx_nhwc_to_nchw_f32(const void* x, float* out, int B, int H, int W, int C, int act_dtype, void* stream);
 
+/* ---- next row (f4): demo preprocessing, reference demo_convnext.py:52-67 --------------------- */
+/* torchaudio.functional.resample (sinc_interp_hann polyphase FIR, demo_convnext.py:53-59) fused with the demo's
+ * constant pad / crop to a fixed clip length (demo_convnext.py:61-67):
+ *   out[b, f*newf + p] = sum_{k<K} taps[k*newf + p] * x[b, f*orig + k - width]      (x = 0 outside [0, L_in))
+ * for output index i < ceil(newf * L_in / orig), zero from there to n_out, cropped at n_out.
+ * orig/newf are the rates divided by their gcd, K = 2*width + orig; taps (K, newf) fp32 is the TRANSPOSED
+ * torchaudio kernel, built on the host (preprocess.sinc_resample_taps).  x (B, ld_in), out (B, ld_out). */
+ACX_API int acx_resample_fit(const float* x, int ld_in, const float* taps, float* out, int ld_out, int B, int L_in,
+                     int orig, int newf, int width, int n_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

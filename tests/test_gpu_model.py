@@ -216,3 +216,47 @@ def test_baseline_config_shapes_front_end_512_and_ragged_200(models, parity_sd):
     ref_small = m(w[[0, 70, 199]].contiguous())
     assert torch.equal(out["clipwise_logits"][[0, 70, 199]], ref_small["clipwise_logits"])
     assert out["clipwise_output"].shape == (200, 527)
+
+
+# ---- SURVEY §8 "next" rows f3 / f4 --------------------------------------------------------------------------------
+@pytest.mark.parametrize("orig", [44100, 48000, 16000, 22050, 32000])
+def test_resample_fit_matches_torchaudio_then_pad_crop(orig):
+    """acx_resample_fit vs torchaudio.functional.resample on the CPU (what demo_convnext.py:52-67 does), including
+    the constant pad (short clip) and the crop (long clip) to a fixed length, several channels as the batch."""
+    TAF = pytest.importorskip("torchaudio.functional")
+    g = torch.Generator().manual_seed(orig)
+    for secs, n_out in ((0.73, 32000), (1.9, 32000), (1.0, None)):
+        L = int(orig * secs) + 3
+        wave = torch.randn(2, L, generator=g) * 0.3
+        ref = TAF.resample(wave, orig, 32000)
+        if n_out is not None:
+            ref = torch.nn.functional.pad(ref, (0, max(n_out - ref.shape[-1], 0)))[:, :n_out]
+        got = acx.preprocess.resample_fit(wave.to(DEV), orig, 32000, n_out).cpu()
+        assert got.shape == ref.shape
+        assert (got - ref).abs().max().item() < 2e-6 * max(1.0, ref.abs().max().item()) * 5      # fp32 summation order
+
+
+def test_resample_rejects_bad_arguments():
+    from audioset_convnext_inf_b200 import _native as N
+    t = torch.zeros(16, device=DEV)
+    rc = N.load().acx_resample_fit(t.data_ptr(), 16, t.data_ptr(), t.data_ptr(), 8, 1, 16, 0, 2, 3, 16, 0)
+    assert rc != 0 and "rates" in N.last_error()
+    rc = N.load().acx_resample_fit(t.data_ptr(), 8, t.data_ptr(), t.data_ptr(), 16, 1, 16, 3, 2, 3, 16, 0)
+    assert rc != 0 and "pitch" in N.last_error()
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_extract_clipwise_buckets_equal_per_clip_loop(models, prec):
+    """extract.extract_clipwise (exact-length buckets, batched) returns, in input order, exactly what the reference's
+    per-file loop (pytorch/extract_embeddings.py:64-92: one forward per clip) would: per-clip results do not depend
+    on the batch they ran in."""
+    m = models[prec]
+    g = torch.Generator().manual_seed(11)
+    lengths = [40000, 64000, 40000, 33333, 64000, 40000, 33333]
+    waves = [(torch.randn(n, generator=g) * 0.1).numpy() for n in lengths]
+    res = acx.extract.extract_clipwise(m, waves, max_batch=2, want=("clipwise_logits", "scene_embeddings"))
+    for i, w in enumerate(waves):
+        with torch.no_grad():
+            one = m.forward_all(torch.from_numpy(w)[None].to(DEV))
+        assert torch.equal(res["clipwise_logits"][i], one["clipwise_logits"][0].float().cpu())
+        assert torch.equal(res["scene_embeddings"][i], one["scene_embeddings"][0].float().cpu())

@@ -136,3 +136,48 @@ def test_gelu_fit_against_exact_erf():
     fast = 0.5 * x * (1 + torch.tanh(inner))
     exact = torch.nn.functional.gelu(x.double())
     assert (fast.double() - exact).abs().max() < 4e-5
+
+
+# ---- SURVEY §8 "next" rows: demo preprocessing (f4), length bucketing (f3), checkpoint converter (f2) -------------
+@pytest.mark.parametrize("orig,new", [(44100, 32000), (48000, 32000), (16000, 32000), (22050, 32000), (8000, 32000)])
+def test_resample_taps_equal_torchaudio_kernel(orig, new):
+    """preprocess.sinc_resample_taps restates torchaudio's polyphase kernel (what demo_convnext.py:53-59 applies)."""
+    import math
+    F = pytest.importorskip("torchaudio.functional.functional")
+    k, w = F._get_sinc_resample_kernel(orig, new, math.gcd(orig, new), dtype=torch.float32)
+    taps, width, o, n = acx.preprocess.sinc_resample_taps(orig, new)
+    assert (width, o, n) == (w, orig // math.gcd(orig, new), new // math.gcd(orig, new))
+    assert taps.shape == (2 * width + o, n)
+    assert torch.equal(taps.t().contiguous(), k[:, 0, :])
+
+
+def test_resample_fit_refuses_cpu_tensors():
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        acx.preprocess.resample_fit(torch.zeros(1, 1000), 44100)
+
+
+def test_length_buckets_group_exact_lengths_in_order():
+    from audioset_convnext_inf_b200.extract import length_buckets
+    b = length_buckets([5, 7, 5, 5, 7, 9], max_batch=2)
+    assert b == [(5, [0, 2]), (5, [3]), (7, [1, 4]), (9, [5])]
+    assert length_buckets([], 4) == []
+
+
+def test_checkpoint_converter_round_trip(tmp_path):
+    """tools/convert_checkpoint.py (reference convert_pytorch_ckpt_to_safetensors.py): .pth {"model": sd} -> strict
+    safetensors with the 190 reference keys, loadable again by from_pretrained."""
+    import importlib.util
+    from safetensors.torch import load_file
+    spec = importlib.util.spec_from_file_location(
+        "convert_checkpoint", os.path.join(os.path.dirname(os.path.dirname(__file__)), "tools", "convert_checkpoint.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    sd = weights.make_state_dict("parity", 3)
+    src, dst = tmp_path / "ckpt.pth", tmp_path / "model.safetensors"
+    torch.save({"model": sd}, src)
+    mod.convert(str(src), str(dst))
+    back = load_file(str(dst))
+    assert set(back) == set(sd) and len(back) == 190
+    assert all(torch.equal(back[k], sd[k]) for k in sd)
+    m = acx.ConvNeXt.from_pretrained(str(dst))
+    assert all(torch.equal(v, sd[k]) for k, v in m.state_dict().items())
