@@ -260,3 +260,22 @@ def test_extract_clipwise_buckets_equal_per_clip_loop(models, prec):
             one = m.forward_all(torch.from_numpy(w)[None].to(DEV))
         assert torch.equal(res["clipwise_logits"][i], one["clipwise_logits"][0].float().cpu())
         assert torch.equal(res["scene_embeddings"][i], one["scene_embeddings"][0].float().cpu())
+
+
+def test_demo_script_runs_resample_pad_and_three_outputs(tmp_path):
+    """demo.py (counterpart of demo_convnext.py) end to end on a 16 kHz, 3 s wav: resample + pad on the GPU, tags,
+    scene and frame embeddings with the reference's shapes."""
+    import subprocess
+    import sys
+    from scipy.io import wavfile
+    rng = np.random.default_rng(0)
+    wav = tmp_path / "clip16k.wav"
+    wavfile.write(wav, 16000, (rng.standard_normal(48000) * 3000).astype(np.int16))
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "demo.py"), "--wav", str(wav)], capture_output=True, text=True,
+                       timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "Resampling from 16000 to 32000 Hz" in r.stdout
+    assert "logits size: (1, 527)" in r.stdout
+    assert "Scene embedding, shape: (1, 768)" in r.stdout
+    assert "Frame-level embeddings, shape: (1, 768, 31, 7)" in r.stdout
