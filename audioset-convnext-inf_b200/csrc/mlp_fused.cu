@@ -399,7 +399,16 @@ __global__ void __launch_bounds__(512, 1)
 // the x tile out.  (The streaming variant above re-read 147 KB of weights from L2 per 128-row tile and, with a ring only
 // one hidden chunk deep, exposed one L2 round trip per chunk: 12.7 k cycles per tile against ~2.3 k of MMA work.)
 // K = 96 is split 64 + 32: the first 64 columns use 128B-swizzled tiles, the 32-column tail 64B-swizzled tiles, so no
-// shared memory is spent on zero padding (W1 48 + 24 KB, W2 72 KB, y tile 16 + 8 KB, hidden tile 32 KB).
+// shared memory is spent on zero padding (W1 48 + 24 KB, W2 72 KB, y tile 16 + 8 KB, hidden buffers 2 x 16 KB).
+//
+// Schedule (second version, driven by clock traces -- tools/trace_mlp.py -- and an ncu source-level capture):
+//   * the 384 hidden columns are six chunks of 64; epilogue-1 group 0 (warps 4-7) takes the even chunks, group 1
+//     (warps 8-11) the odd ones, each into its OWN 128 x 64 hidden buffer (one GEMM2 k-block);
+//   * TMEM: D2 x 2 (columns 0 and 128: epilogue-2 of tile i overlaps GEMM2 of tile i+1), D1 x 4 (64 columns each,
+//     from column 256);
+//   * the MMA thread runs one flat loop over all chunks of all its tiles:  G2(g), then G1(g+4)  -- GEMM1 stays four
+//     chunks ahead across tile boundaries, GEMM2 is issued as soon as its hidden buffer is full;
+//   * the GELU is software-pipelined in 16-column quarters (common.cuh: gelu_stage_ta4 / gelu_stage_c8_twice_bf16).
 // =====================================================================================================================
 #define ACX_TRACE(role, ev)                                                                    \
   do {                                                                                         \
