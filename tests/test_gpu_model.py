@@ -192,6 +192,9 @@ def test_edge_shapes(models, prec):
     fr = m.forward_frame_embeddings(short)
     ref = O.forward_frame_embeddings(short.cpu(), weights.make_state_dict("parity", 8))
     assert fr.shape == ref.shape and fr.shape[2] >= 1
+    empty = m(torch.zeros(0, L, device=DEV))                         # empty batch: empty outputs, no launch
+    assert empty["clipwise_output"].shape == (0, 527) and empty["clipwise_logits"].shape == (0, 527)
+    assert m.forward_scene_embeddings(torch.zeros(0, L, device=DEV)).shape == (0, 768)
     with pytest.raises(ValueError):
         m(torch.zeros(1, 2000, device=DEV))                          # too short for the trunk
     with pytest.raises(ValueError):
