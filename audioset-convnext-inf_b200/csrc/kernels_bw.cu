@@ -263,13 +263,16 @@ __global__ void __launch_bounds__(S* C / 2, dw_min_blocks(S* C / 2))
   const bool left_ok = w0 > 0, right_ok = w0 + 7 < W;
   const PT* x0 = xp + ((ptrdiff_t)w0 - 3) * TPS;   // never dereferenced where the predicates are false
   auto load_row = [&](int ih, PT(&dst)[13]) {
+    // A row outside the image is never USED (its FMA block is skipped below), so it needs no zero fill: its loads
+    // are redirected to row 0 and issued unconditionally -- 7 of the 13 loads lose their predicate and the MOV that
+    // zeroed the destination.  Only the 3 + 3 column-halo words are predicated (they do enter the FMAs).
     const bool row_ok = ih >= 0 && ih < H;
     const PT* row = x0 + (size_t)(row_ok ? ih : 0) * W * TPS;
-    const bool pl = row_ok && left_ok, pr = row_ok && right_ok;
 #pragma unroll
     for (int j = 0; j < 13; ++j) {
-      const bool ok = j < 3 ? pl : (j >= 10 ? pr : row_ok);
-      dst[j] = ok ? __ldg(row + j * TPS) : PT{};
+      if (j < 3) dst[j] = left_ok ? __ldg(row + j * TPS) : PT{};
+      else if (j >= 10) dst[j] = right_ok ? __ldg(row + j * TPS) : PT{};
+      else dst[j] = __ldg(row + j * TPS);
     }
   };
   // The first PF input rows are requested BEFORE the tap fill so that their L2/HBM latency overlaps the fill's own
