@@ -762,6 +762,10 @@ static int dispatch_dwconv(const void* x, const void* w, const float* bias, cons
 
 }  // namespace acx
 
+namespace acx {
+int launch_stem_umma(const float* logmel, const float* w, const float* bias, const float* ln_w, const float* ln_b,
+                     void* out, int B, int T, int n_mels, cudaStream_t st);   // stem_umma.cu
+}
 using namespace acx;
 
 template <typename TIn>
@@ -815,6 +819,10 @@ int acx_stem(const float* logmel, const float* w, const float* bias, const float
   const long long total = (long long)B * H0 * W0;
   const int blocks = (int)((total + 127) / 128);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  // bf16 mode: tensor-core stem (stem_umma.cu); ACX_STEM=simt selects the CUDA-core kernel for A/B timing
+  static const bool stem_simt = [] { const char* e = getenv("ACX_STEM"); return e && e[0] == 's'; }();
+  if (act_dtype == ACX_BF16 && !stem_simt)
+    return launch_stem_umma(logmel, w, bias, ln_w, ln_b, out, B, T, n_mels, st);
   if (act_dtype == ACX_BF16) {
     const int smem = 19 * 96 * 4 + 4 * 32 * (96 * 2 + 16);
     stem_kernel<bf16><<<blocks, 128, smem, st>>>(logmel, w, bias, ln_w, ln_b, reinterpret_cast<bf16*>(out), B, T,

@@ -98,6 +98,34 @@ def test_stem(sd, dtype):
     assert (out.float().cpu() - ref).abs().max() < tol
 
 
+@pytest.mark.parametrize("B,T", [(1, 37), (8, 1001), (24, 1001)])
+def test_stem_tensor_core_equals_cuda_core_up_to_one_bf16_ulp(sd, B, T):
+    """bf16 mode runs the stem as a split-precision tcgen05 GEMM (stem_umma.cu), fp32 mode on the CUDA cores: the
+    bf16 output must be the fp32 result rounded to bf16, give or take one ulp where the fp32 value sits on a rounding
+    boundary.  (8 / 24 clips of 10 s = 882 / 2646 tiles: 2-6 tiles per persistent CTA, ragged last tile at T = 37.)"""
+    g = torch.Generator().manual_seed(B * 1000 + T)
+    lm = (torch.randn(B, T, 224, generator=g) * 2).to(DEV)
+    H0 = (T + 4) // 4 + 1
+    w = sd["downsample_layers.0.0.weight"].reshape(96, 16).t().contiguous().to(DEV)
+    args = [sd[k].to(DEV) for k in ("downsample_layers.0.0.bias", "downsample_layers.0.1.weight",
+                                    "downsample_layers.0.1.bias")]
+    outs = {}
+    for dtype in (torch.float32, torch.bfloat16):
+        out = torch.empty(B, H0, 56, 96, device=DEV, dtype=dtype)
+        N.call("acx_stem", lm.data_ptr(), w.data_ptr(), args[0].data_ptr(), args[1].data_ptr(), args[2].data_ptr(),
+               out.data_ptr(), B, T, 224, _adt(dtype), _st())
+        outs[dtype] = out
+    torch.cuda.synchronize()
+    ref = outs[torch.float32]
+    got = outs[torch.bfloat16].float()
+    ulp = torch.maximum(ref.abs(), torch.tensor(1e-30, device=DEV)).log2().floor().exp2() * 2.0 ** -7
+    diff = (got - ref).abs()
+    # the split-precision product carries ~16 operand bits, so ~1e-5 relative noise reaches the pre-rounding value and
+    # about half a percent of the elements (those within that distance of a bf16 rounding boundary) round the other way
+    assert (diff <= 0.5 * ulp * 1.02 + 2e-5).float().mean().item() > 0.99
+    assert (diff <= 1.01 * ulp + 2e-5).all()        # never off by more than one ulp (+ fp32 noise next to zero)
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("stage,H", [(0, 13), (1, 9), (2, 7), (3, 5), (3, 31)])
 def test_dwconv_ln(sd, stage, H, dtype):
