@@ -123,7 +123,9 @@ def test_stem_tensor_core_equals_cuda_core_up_to_one_bf16_ulp(sd, B, T):
     # the split-precision product carries ~16 operand bits, so ~1e-5 relative noise reaches the pre-rounding value and
     # about half a percent of the elements (those within that distance of a bf16 rounding boundary) round the other way
     assert (diff <= 0.5 * ulp * 1.02 + 2e-5).float().mean().item() > 0.99
-    assert (diff <= 1.01 * ulp + 2e-5).all()        # never off by more than one ulp (+ fp32 noise next to zero)
+    # never off by more than one ulp; next to zero (LayerNorm cancellation) the 16-bit operand split leaves an
+    # ABSOLUTE noise of ~3e-5 (measured: 4 of 10.8 M elements between 2e-5 and 3e-5), far below bf16 resolution at |y| ~ 1
+    assert (diff <= 1.01 * ulp + 1e-4).all()
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
