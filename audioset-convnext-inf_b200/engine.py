@@ -4,7 +4,8 @@ Everything that touches numbers runs in libacx.so (hand-written sm_100a CUDA beh
 include/acx.h); PyTorch only owns device memory and the stream.  Two arithmetic modes:
 
   "bf16"  activations / GEMM operands bf16, fp32 accumulation in TMEM (tcgen05), fp32 LayerNorm
-          statistics; the front end runs split-bf16 (x3) so the log-mel keeps fp32-level accuracy.
+          statistics; the front end runs split precision (x3: scaled fp16 pairs for the DFT, bf16 pairs for the mel
+          product) so the log-mel keeps fp32-level accuracy.
   "fp32"  the fp32-accurate mode: same bandwidth kernels instantiated for float, SIMT fp32 GEMMs.
 
 Kernel order per chunk of clips (reference convnext.py:287-331, forward_features :269-285):
