@@ -11,8 +11,8 @@
 //   3. every thread reads ITS pixel's 96 channels back with tcgen05.ld, adds the bias, does the LayerNorm entirely in
 //      registers (two-pass variance, no cross-thread traffic), packs bf16 and stages the row in smem (the A tiles'
 //      space: the MMAs have completed), from where the warp's 32 contiguous rows are stored with coalesced 16-byte writes.
-// The next tile's patch is requested before the epilogue, and 3 CTAs share an SM, so HBM latency, MMA and epilogue of
-// different tiles overlap.
+// The next tile's patch is requested before the epilogue, and 4 CTAs share an SM (47 KB of smem and 128 TMEM columns
+// each), so HBM latency, MMA and epilogue of different tiles overlap.
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -21,7 +21,7 @@ namespace acx {
 struct StemCfg {
   static constexpr int CO = 96, BM = 128;
   static constexpr int A_TILE = BM * 128;              // 128 rows x 128 B (only 32 B per row carry K = 16)
-  static constexpr int W_TILE = CO * 128;
+  static constexpr int W_TILE = CO * 64;               // 96 rows x 64 B, SWIZZLE_64B (the 16 taps fill half a row)
   static constexpr int OFF_AHI = 0;
   static constexpr int OFF_ALO = OFF_AHI + A_TILE;
   static constexpr int OFF_WHI = OFF_ALO + A_TILE;     // 32 KB
@@ -42,7 +42,7 @@ __device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t& hi, uin
   lo = (uint32_t)__bfloat16_as_ushort(al) | ((uint32_t)__bfloat16_as_ushort(bl) << 16);
 }
 
-__global__ void __launch_bounds__(128, 3)
+__global__ void __launch_bounds__(128, 4)
     stem_umma_kernel(const float* __restrict__ logmel, const float* __restrict__ w, const float* __restrict__ bias,
                      const float* __restrict__ ln_w, const float* __restrict__ ln_b, bf16* __restrict__ out, int Tn,
                      int n_mels, int H0, int W0, long long total) {
@@ -55,14 +55,14 @@ __global__ void __launch_bounds__(128, 3)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_done + 1);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-  // ---- once per CTA: split weights (K-major rows of 16 taps, 128B swizzle), vectors, barrier, TMEM -------------------
+  // ---- once per CTA: split weights (K-major rows of 16 taps, 64B swizzle), vectors, barrier, TMEM --------------------
   if (tid < CO) {
     uint32_t hi[8], lo[8];
 #pragma unroll
     for (int k = 0; k < 16; k += 2) split_bf16x2(w[k * CO + tid], w[(k + 1) * CO + tid], hi[k / 2], lo[k / 2]);
-    const int sw = tid & 7;
-    uint8_t* rh = smem + Cfg::OFF_WHI + tid * 128;
-    uint8_t* rl = smem + Cfg::OFF_WLO + tid * 128;
+    const int sw = (tid >> 1) & 3;                       // SWIZZLE_64B: 16-byte chunk j of row r sits at j ^ ((r >> 1) & 3)
+    uint8_t* rh = smem + Cfg::OFF_WHI + tid * 64;
+    uint8_t* rl = smem + Cfg::OFF_WLO + tid * 64;
     *reinterpret_cast<uint4*>(rh + ((0 ^ sw) << 4)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
     *reinterpret_cast<uint4*>(rh + ((1 ^ sw) << 4)) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
     *reinterpret_cast<uint4*>(rl + ((0 ^ sw) << 4)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
@@ -88,8 +88,8 @@ __global__ void __launch_bounds__(128, 3)
   const uint32_t sbase = ptx::smem_u32(smem);
   const uint64_t dAhi = ptx::umma_desc_sw128_kmajor(sbase + Cfg::OFF_AHI);
   const uint64_t dAlo = ptx::umma_desc_sw128_kmajor(sbase + Cfg::OFF_ALO);
-  const uint64_t dWhi = ptx::umma_desc_sw128_kmajor(sbase + Cfg::OFF_WHI);
-  const uint64_t dWlo = ptx::umma_desc_sw128_kmajor(sbase + Cfg::OFF_WLO);
+  const uint64_t dWhi = ptx::umma_desc_sw64_kmajor(sbase + Cfg::OFF_WHI);
+  const uint64_t dWlo = ptx::umma_desc_sw64_kmajor(sbase + Cfg::OFF_WLO);
   constexpr uint32_t idesc = ptx::umma_idesc_bf16(Cfg::BM, CO);
 
   const long long num_tiles = (total + Cfg::BM - 1) / Cfg::BM;
@@ -212,7 +212,7 @@ int launch_stem_umma(const float* logmel, const float* w, const float* bias, con
   ACX_CUDA(cudaGetDevice(&dev));
   ACX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const long long tiles = (total + Cfg::BM - 1) / Cfg::BM;
-  const long long want = 3LL * sms;                              // 3 resident CTAs per SM
+  const long long want = 4LL * sms;                              // 4 resident CTAs per SM (4 x 128 TMEM columns)
   const int grid = (int)(tiles < want ? tiles : want);
   stem_umma_kernel<<<grid, 128, Cfg::SMEM_BYTES, st>>>(logmel, w, bias, ln_w, ln_b, reinterpret_cast<bf16*>(out), T,
                                                        n_mels, H0, W0, total);
