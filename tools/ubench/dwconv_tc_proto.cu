@@ -20,6 +20,7 @@ constexpr int B_TILE = 64 * 128;              // 8 KB
 __host__ __device__ inline int xval(int c, int r, int w) { return ((c * 7 + r * 3 + w * 5) % 9) - 4; }       // [-4, 4]
 __host__ __device__ inline int tapval(int c, int dy, int dx) { return ((c * 5 + dy * 3 + dx) % 7) - 3; }      // [-3, 3]
 
+template <int NMMA>
 __global__ void __launch_bounds__(128) k(float* out, long long* cyc) {
   extern __shared__ uint8_t raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
@@ -51,7 +52,7 @@ __global__ void __launch_bounds__(128) k(float* out, long long* cyc) {
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem = *slot;
-  constexpr uint32_t idesc = ptx::umma_idesc_bf16(BM, 64);
+  constexpr uint32_t idesc = ptx::umma_idesc_bf16(BM, NMMA);   // NMMA < 64: timing only (narrower stages)
   long long t_bgen = 0, t_mma = 0;
   for (int c = 0; c < CH; ++c) {
     // ---- band matrices of channel c: only the 7 diagonals change (n = w_out row, k = w_in column) ------------------
@@ -72,11 +73,15 @@ __global__ void __launch_bounds__(128) k(float* out, long long* cyc) {
     if (tid == 0) {
       ptx::tc_fence_after();
       const uint32_t d = tmem + c * 64;
-      for (int dy = 0; dy < 7; ++dy) {
-        const uint64_t da = ptx::umma_desc_sw128_kmajor(ptx::smem_u32(sA + c * A_TILE) + dy * 128);
-        const uint64_t db = ptx::umma_desc_sw128_kmajor(ptx::smem_u32(sB + dy * B_TILE));
-        for (int kk = 0; kk < 4; ++kk) ptx::umma_bf16(d, da + 2 * kk, db + 2 * kk, idesc, (dy | kk) ? 1u : 0u);
-      }
+      // descriptors differ only in the 14-bit start-address field (units of 16 B): +8 per row, +2 per K step, so the
+      // 28 MMAs are issued back to back with one add each (built per MMA they cost ~65 cycles apiece -- issue-bound)
+      const uint64_t da0 = ptx::umma_desc_sw128_kmajor(ptx::smem_u32(sA + c * A_TILE));
+      const uint64_t db0 = ptx::umma_desc_sw128_kmajor(ptx::smem_u32(sB));
+#pragma unroll
+      for (int dy = 0; dy < 7; ++dy)
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+          ptx::umma_bf16(d, da0 + dy * 8 + 2 * kk, db0 + dy * (B_TILE / 16) + 2 * kk, idesc, (dy | kk) ? 1u : 0u);
       ptx::umma_commit(bar);
     }
     ptx::mbar_wait(bar, c & 1);          // B is single-buffered here: wait before the next channel rewrites it
@@ -115,9 +120,17 @@ int main() {
   cudaMallocManaged(&out, CH * 128 * 64 * sizeof(float));
   cudaMallocManaged(&cyc, 3 * sizeof(long long));
   const int smem = CH * A_TILE + 7 * B_TILE + 64 + 1024;
-  cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaFuncSetAttribute(k<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaFuncSetAttribute(k<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaFuncSetAttribute(k<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   for (int rep = 0; rep < 2; ++rep) {
-    k<<<1, 128, smem>>>(out, cyc);
+    k<32><<<1, 128, smem>>>(out, cyc);
+    cudaDeviceSynchronize();
+    if (rep) printf("timing only, M128 N32 K16: 28 MMAs issue->complete %lld cycles (%.1f per MMA)\n", cyc[1] / CH, cyc[1] / CH / 28.0);
+    k<16><<<1, 128, smem>>>(out, cyc);
+    cudaDeviceSynchronize();
+    if (rep) printf("timing only, M128 N16 K16: 28 MMAs issue->complete %lld cycles (%.1f per MMA)\n", cyc[1] / CH, cyc[1] / CH / 28.0);
+    k<64><<<1, 128, smem>>>(out, cyc);
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) {
       printf("CUDA error %s\n", cudaGetErrorString(e));
