@@ -445,7 +445,7 @@ __global__ void __launch_bounds__(S* C / 2, dw_min_blocks(S* C / 2))
 // works on NPIX pixels at once so their loads overlap.  (First version: 4-byte loads, 28 % of HBM roofline.)
 // =============================================================================================
 template <typename T, int C>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
     ln_patchify_kernel(const T* __restrict__ x, const float* __restrict__ ln_w, const float* __restrict__ ln_b,
                        T* __restrict__ a, int B, int H, int W) {
   constexpr int CH = 24;                      // channels per lane
@@ -458,12 +458,10 @@ __global__ void __launch_bounds__(256)
   const int Ho = H / 2, Wo = W / 2;
   const long long total = (long long)B * Ho * 2 * Wo * 2;
   const long long grp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / LPP;
-  float g[CH], be[CH];
-#pragma unroll
-  for (int j = 0; j < CH; j += 4) {
-    *reinterpret_cast<float4*>(&g[j]) = *reinterpret_cast<const float4*>(ln_w + lig * CH + j);
-    *reinterpret_cast<float4*>(&be[j]) = *reinterpret_cast<const float4*>(ln_b + lig * CH + j);
-  }
+  // the affine vectors are read (L1-resident) where they are used instead of living in 48 registers across the
+  // loads: 3 blocks per SM instead of 2 keep more bytes in flight (ncu: 21 % occupancy, 42-59 % of HBM before)
+  const float* gp = ln_w + lig * CH;
+  const float* bp = ln_b + lig * CH;
   float v[NPIX][CH];
   size_t dst_off[NPIX];
   bool ok[NPIX];
@@ -519,16 +517,20 @@ __global__ void __launch_bounds__(256)
         uint4 o4;
         if (sizeof(T) == 2) {
           const int k = 8 * j;
-          o4.x = Pair<bf16>::pack(v[q][k + 0] * rstd * g[k + 0] + be[k + 0], v[q][k + 1] * rstd * g[k + 1] + be[k + 1]);
-          o4.y = Pair<bf16>::pack(v[q][k + 2] * rstd * g[k + 2] + be[k + 2], v[q][k + 3] * rstd * g[k + 3] + be[k + 3]);
-          o4.z = Pair<bf16>::pack(v[q][k + 4] * rstd * g[k + 4] + be[k + 4], v[q][k + 5] * rstd * g[k + 5] + be[k + 5]);
-          o4.w = Pair<bf16>::pack(v[q][k + 6] * rstd * g[k + 6] + be[k + 6], v[q][k + 7] * rstd * g[k + 7] + be[k + 7]);
+          const float4 g0 = __ldg(reinterpret_cast<const float4*>(gp + k)), g1 = __ldg(reinterpret_cast<const float4*>(gp + k + 4));
+          const float4 b0 = __ldg(reinterpret_cast<const float4*>(bp + k)), b1 = __ldg(reinterpret_cast<const float4*>(bp + k + 4));
+          o4.x = Pair<bf16>::pack(v[q][k + 0] * rstd * g0.x + b0.x, v[q][k + 1] * rstd * g0.y + b0.y);
+          o4.y = Pair<bf16>::pack(v[q][k + 2] * rstd * g0.z + b0.z, v[q][k + 3] * rstd * g0.w + b0.w);
+          o4.z = Pair<bf16>::pack(v[q][k + 4] * rstd * g1.x + b1.x, v[q][k + 5] * rstd * g1.y + b1.y);
+          o4.w = Pair<bf16>::pack(v[q][k + 6] * rstd * g1.z + b1.z, v[q][k + 7] * rstd * g1.w + b1.w);
         } else {
           const int k = 4 * j;
-          o4.x = __float_as_uint(v[q][k + 0] * rstd * g[k + 0] + be[k + 0]);
-          o4.y = __float_as_uint(v[q][k + 1] * rstd * g[k + 1] + be[k + 1]);
-          o4.z = __float_as_uint(v[q][k + 2] * rstd * g[k + 2] + be[k + 2]);
-          o4.w = __float_as_uint(v[q][k + 3] * rstd * g[k + 3] + be[k + 3]);
+          const float4 g0 = __ldg(reinterpret_cast<const float4*>(gp + k));
+          const float4 b0 = __ldg(reinterpret_cast<const float4*>(bp + k));
+          o4.x = __float_as_uint(v[q][k + 0] * rstd * g0.x + b0.x);
+          o4.y = __float_as_uint(v[q][k + 1] * rstd * g0.y + b0.y);
+          o4.z = __float_as_uint(v[q][k + 2] * rstd * g0.z + b0.z);
+          o4.w = __float_as_uint(v[q][k + 3] * rstd * g0.w + b0.w);
         }
         reinterpret_cast<uint4*>(dst)[j] = o4;
       }
