@@ -33,6 +33,19 @@ const char* last_error();
     }                                                                               \
   } while (0)
 
+// Opt a kernel into more than 48 KB of dynamic shared memory.  The attribute is PER DEVICE, so it is remembered with one
+// bit per device (a process that drives several GPUs would otherwise configure only the first one it used).
+#define ACX_SET_MAX_SMEM(kern, bytes)                                                               \
+  do {                                                                                              \
+    static unsigned long long acx_done_ = 0;                                                        \
+    int acx_dev_ = 0;                                                                               \
+    ACX_CUDA(cudaGetDevice(&acx_dev_));                                                             \
+    if (acx_dev_ >= 64 || !((acx_done_ >> acx_dev_) & 1ull)) {                                      \
+      ACX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (bytes)));   \
+      if (acx_dev_ < 64) acx_done_ |= 1ull << acx_dev_;                                             \
+    }                                                                                               \
+  } while (0)
+
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 

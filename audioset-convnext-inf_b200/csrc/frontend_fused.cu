@@ -308,11 +308,7 @@ extern "C" int acx_frontend_fused(const void* hi, const void* lo, int ld_pad, co
   rc = make_tmap_2d_bf16(&tmMelLo, mel_lo, 64, (uint64_t)n_chunks * 256, 128, 64, fe::MEL_ROWS);
   if (rc != ACX_OK) return rc;
 
-  static bool configured = false;
-  if (!configured) {
-    ACX_CUDA(cudaFuncSetAttribute(frontend_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fe::SMEM_BYTES));
-    configured = true;
-  }
+  ACX_SET_MAX_SMEM(frontend_fused_kernel, fe::SMEM_BYTES);
   FeArgs a;
   a.out = out;
   a.bn_scale = bn_scale;

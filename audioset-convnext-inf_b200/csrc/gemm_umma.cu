@@ -333,11 +333,7 @@ static int launch_umma_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, cons
                             cudaStream_t st) {
   using Cfg = GemmCfg<BN, NEPI, CG>;
   auto kern = umma_gemm_kernel<BN, EPI, NEPI, CG>;
-  static bool configured = false;  // per-instantiation; benign race (idempotent attribute set)
-  if (!configured) {
-    ACX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    configured = true;
-  }
+  ACX_SET_MAX_SMEM(kern, Cfg::SMEM_BYTES);
   ACX_CHECK(g.N * (EPI == ACX_EPI_BIAS_SCALE_RESID ? 8 : 4) <= Cfg::VEC_BYTES, ACX_ERR_UNSUPPORTED,
             "gemm_bf16: N=%d exceeds the per-column vectors staged in shared memory", g.N);
   int dev = 0, sms = 0;

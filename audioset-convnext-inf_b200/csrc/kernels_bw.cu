@@ -712,11 +712,7 @@ static int launch_dwconv(const void* x, const void* w, const float* bias, const 
   constexpr int NV = sizeof(T) == 4 ? 32 : 64;
   constexpr int SMEM = (2 * 49 * (C / 2) + S * (C / 32) * NV + S * NV) * (int)sizeof(float);
   auto kern = dwconv_ln_kernel<T, C, S, PF>;
-  static bool configured = false;
-  if (!configured) {
-    ACX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-    configured = true;
-  }
+  ACX_SET_MAX_SMEM(kern, SMEM);
   const int row_groups = ceil_div(H, DW_R);
   // Row groups per block.  With the first input rows requested ahead of the tap fill (and the next group's rows
   // ahead of the LayerNorm phase) one group per block is fastest everywhere except the tiny stage-4 maps, where the
@@ -831,11 +827,7 @@ int acx_stem(const float* logmel, const float* w, const float* bias, const float
                                                  n_mels, H0, W0);
   } else {
     const int smem = 19 * 96 * 4 + 4 * 32 * (96 * 4 + 16);
-    static bool configured = false;
-    if (!configured) {
-      ACX_CUDA(cudaFuncSetAttribute(stem_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      configured = true;
-    }
+    ACX_SET_MAX_SMEM(stem_kernel<float>, smem);
     stem_kernel<float><<<blocks, 128, smem, st>>>(logmel, w, bias, ln_w, ln_b, reinterpret_cast<float*>(out), B, T,
                                                   n_mels, H0, W0);
   }

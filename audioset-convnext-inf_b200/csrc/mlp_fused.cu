@@ -788,11 +788,7 @@ static int launch_mlp96_resident(const void* y, void* x, const void* w1, const f
   if (rc != ACX_OK) return rc;
   rc = make_tmap_2d_bf16(&tmOut, x, 96, (uint64_t)M, 192, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
   if (rc != ACX_OK) return rc;
-  static bool configured = false;
-  if (!configured) {
-    ACX_CUDA(cudaFuncSetAttribute(mlp_fused96_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    configured = true;
-  }
+  ACX_SET_MAX_SMEM(mlp_fused96_kernel, Cfg::SMEM_BYTES);
   int dev = 0, sms = 0;
   ACX_CUDA(cudaGetDevice(&dev));
   ACX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -823,11 +819,7 @@ static int launch_mlp(const void* y, void* x, const void* w1, const float* b1, c
   rc = make_tmap_2d_bf16(&tmOut, x, C, (uint64_t)M, (uint64_t)C * 2, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
   if (rc != ACX_OK) return rc;
   auto kern = mlp_fused_kernel<C>;
-  static bool configured = false;
-  if (!configured) {
-    ACX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    configured = true;
-  }
+  ACX_SET_MAX_SMEM(kern, Cfg::SMEM_BYTES);
   int dev = 0, sms = 0;
   ACX_CUDA(cudaGetDevice(&dev));
   ACX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));

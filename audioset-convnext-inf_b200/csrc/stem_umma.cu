@@ -203,11 +203,7 @@ int launch_stem_umma(const float* logmel, const float* w, const float* bias, con
   using Cfg = StemCfg;
   const int H0 = (T + 4) / 4 + 1, W0 = n_mels / 4;
   const long long total = (long long)B * H0 * W0;
-  static bool configured = false;
-  if (!configured) {
-    ACX_CUDA(cudaFuncSetAttribute(stem_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    configured = true;
-  }
+  ACX_SET_MAX_SMEM(stem_umma_kernel, Cfg::SMEM_BYTES);
   int dev = 0, sms = 0;
   ACX_CUDA(cudaGetDevice(&dev));
   ACX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
