@@ -58,3 +58,23 @@ def test_sharded_forward_bit_identical_to_single_gpu(n_clips):
         p.join(timeout=60)
     assert all(ok for _, ok, _ in res), res
     assert res[0][2][0] == n_clips
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_devices_in_one_process_give_identical_results():
+    """One process driving cuda:0 and then cuda:1 (not the one-process-per-GPU layout of bench.py): per-device kernel
+    attributes (dynamic shared memory opt-in), tensor maps and workspaces must all follow the model's device."""
+    sys.path.insert(0, ROOT)
+    import audioset_convnext_inf_b200 as acx
+    from oracle import weights
+    sd = weights.make_state_dict("parity", 8)
+    waves = weights.make_waveforms(3, n_samples=64000, kind="noise", seed=9)
+    outs = []
+    for dev in ("cuda:0", "cuda:1"):
+        m = acx.convnext_tiny(drop_path_rate=0.0, after_stem_dim=[252, 56])
+        m.load_state_dict(sd)
+        m = m.to(dev).eval()
+        o = m.forward_all(waves.to(dev))
+        assert all(v.device == torch.device(dev) for v in o.values())
+        outs.append({k: v.cpu() for k, v in o.items()})
+    assert all(torch.equal(outs[0][k], outs[1][k]) for k in outs[0])
