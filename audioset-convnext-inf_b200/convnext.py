@@ -253,9 +253,15 @@ class ConvNeXt(nn.Module):
 def load_checkpoint(model, path, map_location="cpu"):
     """`.safetensors` strict load (CX:507) or a torch `.pth` holding {"model": state_dict}
     (evaluate_convnext_on_audioset.py:36-38)."""
-    with open(path, "rb") as fh:
-        head = fh.read(2)
-    if head == b"PK" or head[:1] == b"\x80":          # torch zip / legacy pickle
+    # Decided by what the file IS, not by its first bytes looking like something: a safetensors file starts with a
+    # little-endian u64 header length whose low bytes can be anything (0x80.., "PK"), so the extension wins, then a
+    # real zip check, then a parse of the safetensors header; only what is left goes to torch.load.
+    import zipfile
+    ext = os.path.splitext(str(path))[1].lower()
+    is_torch = ext in (".pth", ".pt", ".ckpt", ".bin")
+    if not is_torch and ext != ".safetensors":
+        is_torch = zipfile.is_zipfile(path) or not _looks_like_safetensors(path)
+    if is_torch:
         ckpt = torch.load(path, map_location=map_location, weights_only=True)
         model.load_state_dict(ckpt["model"] if "model" in ckpt else ckpt)
     else:
@@ -263,6 +269,20 @@ def load_checkpoint(model, path, map_location="cpu"):
         st_load_model(model, path)
         model._engine = None
     return model
+
+
+def _looks_like_safetensors(path):
+    import json
+    import struct
+    try:
+        size = os.path.getsize(path)
+        with open(path, "rb") as fh:
+            (n,) = struct.unpack("<Q", fh.read(8))
+            if n <= 0 or n > size - 8 or n > (100 << 20):
+                return False
+            return isinstance(json.loads(fh.read(n)), dict)
+    except Exception:  # noqa: BLE001 -- anything unparsable is not safetensors
+        return False
 
 
 def convnext_tiny(pretrained=False, strict=False, in_22k=False, drop_path_rate=0.1, after_stem_dim=[56],

@@ -7,6 +7,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <atomic>
+
 #include "../../include/acx.h"
 
 namespace acx {
@@ -37,14 +39,29 @@ const char* last_error();
 // bit per device (a process that drives several GPUs would otherwise configure only the first one it used).
 #define ACX_SET_MAX_SMEM(kern, bytes)                                                               \
   do {                                                                                              \
-    static unsigned long long acx_done_ = 0;                                                        \
+    static std::atomic<unsigned long long> acx_done_{0};   /* host threads may drive different GPUs at once */    \
     int acx_dev_ = 0;                                                                               \
     ACX_CUDA(cudaGetDevice(&acx_dev_));                                                             \
-    if (acx_dev_ >= 64 || !((acx_done_ >> acx_dev_) & 1ull)) {                                      \
+    if (acx_dev_ >= 64 || !((acx_done_.load(std::memory_order_acquire) >> acx_dev_) & 1ull)) {      \
       ACX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (bytes)));   \
-      if (acx_dev_ < 64) acx_done_ |= 1ull << acx_dev_;                                             \
+      if (acx_dev_ < 64) acx_done_.fetch_or(1ull << acx_dev_, std::memory_order_release);           \
     }                                                                                               \
   } while (0)
+
+// SM count of the current device (cached per device; the persistent grids are sized from it, never hard-coded)
+static inline int sm_count() {
+  static std::atomic<int> cached[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (dev < 64) {
+    const int c = cached[dev].load(std::memory_order_relaxed);
+    if (c > 0) return c;
+  }
+  int sms = 0;
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) return 148;
+  if (dev < 64) cached[dev].store(sms, std::memory_order_relaxed);
+  return sms;
+}
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }

@@ -358,7 +358,7 @@ static int launch_umma_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, cons
 }
 
 // B operand / output maps and tile-shape dispatch.  A CTA pair (CG = 2) is used when there are enough 256-row tiles to
-// fill the 74 pairs; small problems keep one CTA per 128-row tile.
+// fill every SM pair (74 on a B200; taken from the device, not assumed); small problems keep one CTA per 128-row tile.
 template <int EPI>
 static int dispatch_bn(const CUtensorMap& tmA, const void* W, const GemmArgs& g, cudaStream_t st) {
   int bn = 0;
@@ -370,15 +370,16 @@ static int dispatch_bn(const CUtensorMap& tmA, const void* W, const GemmArgs& g,
   }
   ACX_CHECK(bn != 0, ACX_ERR_UNSUPPORTED, "gemm_bf16: N=%d is not a multiple of 96/128/192/256", g.N);
   static const bool pair_ok = getenv("ACX_GEMM_PAIR") == nullptr || atoi(getenv("ACX_GEMM_PAIR")) != 0;
-  // Wave quantisation: a persistent grid of 74 CTA pairs runs ceil(tiles / 74) rounds of BN-wide tiles, so when both
+  const long long pairs = sm_count() / 2;     // 74 on a B200
+  // Wave quantisation: a persistent grid of `pairs` CTA pairs runs ceil(tiles / pairs) rounds of BN-wide tiles, so when both
   // 256 and 192 divide N the cheaper of  rounds(BN) * BN  wins (ties keep 256: fewer A re-reads).  Stage 3 at 64 clips:
   // N = 768 is 165 tiles = 3 rounds at BN 256 (2.2 needed) but 220 tiles = 3 rounds at BN 192 -- a quarter less work.
   if (pair_ok && bn == 256 && g.N % 192 == 0) {
     const long long mt = ceil_div(g.M, 256);
-    const long long r256 = (mt * (g.N / 256) + 73) / 74 * 256, r192 = (mt * (g.N / 192) + 73) / 74 * 192;
-    if (mt * (g.N / 192) >= 74 && r192 < r256) bn = 192;
+    const long long r256 = (mt * (g.N / 256) + pairs - 1) / pairs * 256, r192 = (mt * (g.N / 192) + pairs - 1) / pairs * 192;
+    if (mt * (g.N / 192) >= pairs && r192 < r256) bn = 192;
   }
-  const bool pair = pair_ok && (bn == 256 || bn == 192) && (long long)ceil_div(g.M, 256) * (g.N / bn) >= 74;
+  const bool pair = pair_ok && (bn == 256 || bn == 192) && (long long)ceil_div(g.M, 256) * (g.N / bn) >= pairs;
   CUtensorMap tmB;
   int rc = make_tmap_2d_bf16(&tmB, W, (uint64_t)g.K, (uint64_t)g.N, (uint64_t)g.K * 2, 64,
                              (uint32_t)(pair ? bn / 2 : bn));

@@ -799,7 +799,11 @@ static int launch_mlp96_resident(const void* y, void* x, const void* w1, const f
   a.b2 = b2;
   a.gamma = gamma;
   a.M = M;
+#ifdef ACX_ENABLE_TRACE   // debug builds only (ACX_NVCC_EXTRA="-DACX_ENABLE_TRACE", tools/trace_mlp.py): a raw device pointer
   a.trace = getenv("ACX_TRACE_PTR") ? reinterpret_cast<unsigned long long*>(strtoull(getenv("ACX_TRACE_PTR"), nullptr, 0)) : nullptr;
+#else                     // from the environment has no place in the production entry point
+  a.trace = nullptr;
+#endif
   mlp_fused96_kernel<<<tiles < sms ? tiles : sms, 512, Cfg::SMEM_BYTES, st>>>(tmYm, tmYt, tmW1m, tmW1t, tmW2, tmOut, a);
   ACX_CUDA(cudaGetLastError());
   return ACX_OK;

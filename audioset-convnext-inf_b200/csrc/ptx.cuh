@@ -40,8 +40,10 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 // (or the hint expires) instead of spinning: a tight try_wait/branch loop in the single-thread producer / MMA warps
 // stole issue slots from the epilogue warps sharing their scheduler and slowed every epilogue step ~5x (in-kernel
 // clock trace, tools/trace_mlp.py).  Watchdog: a mis-programmed pipeline traps (sticky CUDA error) instead of hanging.
-#ifndef ACX_MBAR_SPIN_LIMIT
-#define ACX_MBAR_SPIN_LIMIT 4000u      /* x 10 ms hint */
+#ifndef ACX_MBAR_TIMEOUT_NS
+#define ACX_MBAR_TIMEOUT_NS 20000000000ull      /* 20 s of wall time (globaltimer), not a spin count: under
+                                                   compute-sanitizer try_wait returns early and kernels run ~100x
+                                                   slower, which made a count-based watchdog fire spuriously */
 #endif
 __device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t ticks) {
   uint32_t ok;
@@ -54,13 +56,23 @@ __device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parit
       : "memory");
   return ok != 0;
 }
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
+  uint64_t t0 = 0;
   while (!mbar_try_wait_hint(bar, parity, 0x989680u)) {
-    if (++spins > ACX_MBAR_SPIN_LIMIT) {
-      printf("acx: mbarrier watchdog block=%d thread=%d bar=%u parity=%u\n", (int)blockIdx.x, (int)threadIdx.x,
-             smem_u32(bar), parity);
-      __trap();
+    if ((++spins & 63u) == 0) {                      // the clock is only looked at on the (rare) slow path
+      const uint64_t t = globaltimer_ns();
+      if (t0 == 0) t0 = t;
+      else if (t - t0 > ACX_MBAR_TIMEOUT_NS) {
+        printf("acx: mbarrier watchdog block=%d thread=%d bar=%u parity=%u\n", (int)blockIdx.x, (int)threadIdx.x,
+               smem_u32(bar), parity);
+        __trap();
+      }
     }
   }
 }

@@ -13,15 +13,18 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 static inline PFN_encodeTiled get_encode_tiled() {
-  static PFN_encodeTiled fn = nullptr;
-  if (!fn) {
+  static std::atomic<PFN_encodeTiled> fn{nullptr};        // idempotent lookup; racing threads store the same pointer
+  PFN_encodeTiled f = fn.load(std::memory_order_acquire);
+  if (!f) {
     void* p = nullptr;
     cudaDriverEntryPointQueryResult q;
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<PFN_encodeTiled>(p);
+        q == cudaDriverEntryPointSuccess) {
+      f = reinterpret_cast<PFN_encodeTiled>(p);
+      fn.store(f, std::memory_order_release);
+    }
   }
-  return fn;
+  return f;
 }
 
 // Generic rank-R bf16 map, 128B swizzle, OOB reads return zero.

@@ -12,6 +12,7 @@ Kernel order per chunk of clips (reference convnext.py:287-331, forward_features
   wave_prep -> front end -> stem -> [dwconv_ln -> pwconv1+GELU -> pwconv2+gamma+residual] x (3,3,9,3)
   with ln_patchify + GEMM between stages -> head (pool + LayerNorm + fc + sigmoid) / frame transpose.
 """
+import collections
 import os
 
 import torch
@@ -160,8 +161,11 @@ class Engine:
         self.mlp = mlp or os.environ.get("ACX_MLP", "fused")
         if precision == "fp32":
             self.frontend, self.mlp = "simt", "gemm"
-        self._ws = {}
-        self._graphs = {}
+        # LRU of workspaces keyed by (clips, samples); each owns the CUDA graphs captured over its buffers, so a
+        # variable-length extraction or a ragged last batch neither re-allocates nor re-captures per call
+        self._ws = collections.OrderedDict()
+        self.max_workspaces = int(os.environ.get("ACX_WORKSPACES", 4))
+        self.graph_after = int(os.environ.get("ACX_GRAPH_AFTER", 2))   # capture a shape on its 2nd use, not its 1st
         self.use_graph = os.environ.get("ACX_GRAPH", "1") == "1" and precision == "bf16"
         self._prof = None
         self._prof_only = None
@@ -172,6 +176,7 @@ class Engine:
         key = (n, L)
         ws = self._ws.get(key)
         if ws is not None:
+            self._ws.move_to_end(key)
             return ws
         T, hs = out_time_dims(L)
         dev = self.device
@@ -195,8 +200,10 @@ class Engine:
         ws["logits"] = torch.empty(n, N_CLASSES, device=dev, dtype=torch.float32)
         ws["probs"] = torch.empty(n, N_CLASSES, device=dev, dtype=torch.float32)
         ws["frame"] = torch.empty(n, DIMS[3], hs[3], 7, device=dev, dtype=torch.float32)
-        self._ws.clear()          # keep one shape resident
-        self._graphs.clear()      # captured graphs point into the old workspace
+        ws["graphs"] = {}         # (n, trunk, head, frame) -> (CUDAGraph, launches per replay); dies with the buffers
+        ws["uses"] = {}
+        while len(self._ws) >= max(1, self.max_workspaces):
+            self._ws.popitem(last=False)          # least recently used shape (its graphs go with it)
         self._ws[key] = ws
         return ws
 
@@ -385,11 +392,12 @@ class Engine:
                 self._wave_prep(wave[b0:b0 + n], ws, n, L, st)
                 trunk = need_head or "frame" in want
                 key = (n, L, trunk, need_head, "frame" in want)
-                if self.use_graph and self._prof is None:
-                    g = self._graphs.get(key)
-                    if g is None:
-                        g = self._capture(ws, n, L, *key[2:])
-                        self._graphs[key] = g
+                g = ws["graphs"].get(key) if (self.use_graph and self._prof is None) else None
+                if g is None and self.use_graph and self._prof is None:
+                    ws["uses"][key] = ws["uses"].get(key, 0) + 1
+                    if ws["uses"][key] >= self.graph_after:      # a shape seen once (odd length, ragged tail) runs eagerly
+                        g = ws["graphs"][key] = self._capture(ws, n, L, *key[2:])
+                if g is not None:
                     g[0].replay()
                     self.launches += g[1]
                 else:

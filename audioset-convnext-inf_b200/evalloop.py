@@ -30,16 +30,21 @@ def forward(model, generator, use_torchaudio=False, return_input=False, return_t
     if use_torchaudio:
         raise NotImplementedError("the torchaudio fbank front end (use_torchaudio=True) is out of scope")
     model.eval()
-    batches, inputs, targets = [], [], []
-    for batch_data_dict in generator:
-        hb = _as_host_batch(batch_data_dict["waveform"])
-        batches.append(hb.pin_memory() if torch.cuda.is_available() else hb)
-        if return_input:
-            inputs.append(hb.numpy())
-        if return_target and "target" in batch_data_dict:
-            targets.append(np.asarray(batch_data_dict["target"]))
+    inputs, targets = [], []
+
+    def host_batches():
+        # one batch at a time: the loader (HDF5 reads in the reference) overlaps with the kernels of the previous batch
+        # and nothing but the pipeline's `depth` staging buffers is ever page-locked
+        for batch_data_dict in generator:
+            hb = _as_host_batch(batch_data_dict["waveform"])
+            if return_input:
+                inputs.append(hb.numpy())
+            if return_target and "target" in batch_data_dict:
+                targets.append(np.asarray(batch_data_dict["target"]))
+            yield hb
+
     # batches of equal shape stream through one pipeline; a ragged last batch simply re-allocates its slots
-    results = HostPipeline(model, want=("logits",)).run(batches)
+    results = HostPipeline(model, want=("logits",)).run(host_batches())
     out = {"clipwise_output": np.concatenate([r["probs"].numpy() for r in results], axis=0)}
     if return_input:
         out["waveform"] = np.concatenate(inputs, axis=0)

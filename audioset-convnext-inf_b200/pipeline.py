@@ -29,12 +29,16 @@ class HostPipeline:
         for _ in range(self.depth):
             slots.append(dict(
                 raw=torch.empty(B, L, device=self.dev, dtype=batch.dtype),
+                stage=None,       # pinned staging for pageable inputs, allocated on first need (bounded: depth x batch)
                 h2d=torch.cuda.Event(), done=torch.cuda.Event(), free=torch.cuda.Event(), out=None, host=None))
         self._slots = slots
         self._shape = (B, L, batch.dtype)
 
     def run(self, host_batches):
-        """host_batches: iterable of (B, L) CPU tensors (pinned for true overlap), fp32 or int16.
+        """host_batches: iterable (list or GENERATOR -- batches are pulled one at a time, so a data loader overlaps
+        with the kernels) of (B, L) CPU tensors, fp32 or int16.  Pinned tensors are copied from directly; pageable
+        ones go through `depth` reusable pinned staging buffers owned by the pipeline, so page-locked memory stays
+        bounded by depth x batch whatever the number of batches (the reference streams batch by batch, PU:88-137).
         Returns a list (same order) of dicts of CPU tensors for the requested outputs."""
         if self.model.training:
             raise RuntimeError("inference only: call model.eval() first")
@@ -49,6 +53,13 @@ class HostPipeline:
                 s = self._slots[i % self.depth]
                 if len(pending) >= self.depth:          # slot reuse: its previous result must be retired first
                     self._retire(pending.pop(0), results)
+                if not hb.is_pinned():
+                    if s["stage"] is None:
+                        s["stage"] = torch.empty(hb.shape, dtype=hb.dtype).pin_memory()
+                    else:
+                        s["h2d"].synchronize()                  # the previous H2D out of this staging buffer is done
+                    s["stage"].copy_(hb)
+                    hb = s["stage"]
                 with torch.cuda.stream(self.copy_stream):
                     self.copy_stream.wait_event(s["free"])      # kernels that read this slot's input have finished
                     s["raw"].copy_(hb, non_blocking=True)

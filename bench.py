@@ -112,6 +112,153 @@ def cpu_reference_clips_per_s(state_dict, clips, iters, threads):
     return clips * iters / dt, dt
 
 
+def _time_ms(fn, iters, device):
+    """Median device time of fn() over `iters` runs (CUDA events, sync both sides)."""
+    ts = []
+    for _ in range(iters):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(device)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize(device)
+        ts.append(e0.elapsed_time(e1))
+    return statistics.median(ts)
+
+
+def extras_single_gpu(model, eng, device, peaks):
+    """The other BASELINE.json configs, measured in the same run (rank 0, one GPU):
+    configs[2] front end only at batch 512, configs[0] batch-1 latency, configs[4] batch sweep 1..2048,
+    plus the same-GPU comparator: the reference's ops in stock eager PyTorch (cuDNN / cuBLAS) on this B200."""
+    out = {}
+    g = torch.Generator(device=device).manual_seed(77)
+
+    def clips(b):
+        return (torch.randn(b, CLIP_SAMPLES, device=device, generator=g) * 0.1).clamp_(-1.0, 1.0)
+
+    # ---- configs[2]: front end only, 512 clips --------------------------------------------------------------------
+    w512 = clips(512)
+    eng.run(w512[:64], want=("logmel",))
+    eng.run(w512, want=("logmel",))
+    api_ms = _time_ms(lambda: eng.run(w512, want=("logmel",)), 5, device)
+    eng.start_timing(None)
+    eng.run(w512, want=("logmel",))
+    kern = {}
+    for tag, ms in eng.stop_timing():
+        kern[tag] = kern.get(tag, 0.0) + ms
+    k_ms = sum(kern.values())
+    T = CLIP_SAMPLES // 320 + 1
+    bytes_alg = 512 * (CLIP_SAMPLES * 4.0 + T * 224 * 4.0)          # fp32 waveform in, fp32 log-mel out (as built)
+    flops = 512 * T * 2.0 * (1024 * 2 * 513 + 513 * 224)
+    out["frontend_only"] = {
+        "workload": "STFT(1024, hop 320) + 224-bin log-mel + bn0, 512 synthetic 10 s clips (BASELINE.json configs[2])",
+        "clips_per_s_kernels": round(512 / (k_ms * 1e-3), 1), "kernels_ms": {k: round(v, 4) for k, v in kern.items()},
+        "clips_per_s_api": round(512 / (api_ms * 1e-3), 1), "api_ms": round(api_ms, 3),
+        "api_note": "Engine.run(want=('logmel',)) also copies each chunk's log-mel into the caller's tensor",
+        "hbm_gbs": round(bytes_alg / (k_ms * 1e-3) / 1e9, 1), "hbm_frac": round(bytes_alg / (k_ms * 1e-3) / 1e9 / peaks["hbm"], 4),
+        "tflops_dense_dft": round(flops / (k_ms * 1e-3) / 1e12, 1),
+        "tensor_frac": round(flops / (k_ms * 1e-3) / 1e12 / peaks["tensor_sust"], 4)}
+    del w512
+
+    # ---- configs[0] / configs[4]: batch-1 latency and the batch sweep (tagging + scene embedding) --------------------
+    sweep = []
+    for b in (1, 8, 64, 256, 1024, 2048):
+        w = clips(b)
+        for _ in range(3):
+            eng.run(w, want=("logits", "scene"))
+        ms = _time_ms(lambda: eng.run(w, want=("logits", "scene")), 20 if b <= 64 else 3, device)
+        sweep.append({"batch": b, "ms": round(ms, 4), "clips_per_s": round(b / (ms * 1e-3), 1)})
+        del w
+    out["latency_b1"] = {"ms": sweep[0]["ms"], "workload": "one 10 s clip, tagging + scene embedding, CUDA-graph replay "
+                         "(BASELINE.json configs[0] shape on the GPU)"}
+    out["sweep"] = {"workload": "tagging + scene embeddings, device-resident synthetic clips (BASELINE.json configs[4])",
+                    "points": sweep}
+
+    # ---- same-GPU comparator: the reference's own ops, stock eager PyTorch on this B200 -----------------------------
+    from oracle import convnext_oracle as O
+    sd = {k: v.detach().to(device) for k, v in model.state_dict().items()}
+    w = clips(BATCH)
+    eager = {}
+    with torch.no_grad(), O.on_device(device):
+        def fp32():
+            return O.forward(w, sd)
+
+        def amp():
+            lm = O.frontend(w, sd)                                   # front end kept fp32 (bf16 DFT is 35 dB off)
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                emb = O.forward_features(lm[:, None], sd)
+                return torch.nn.functional.linear(emb, sd["head_audioset.weight"], sd["head_audioset.bias"])
+        for name, fn in (("fp32", fp32), ("bf16_autocast", amp)):
+            try:
+                fn()
+                fn()
+                ms = _time_ms(fn, 5, device)
+                eager[name] = {"ms_per_64_clips": round(ms, 3), "clips_per_s": round(BATCH / (ms * 1e-3), 1)}
+            except Exception as e:  # noqa: BLE001 -- a measurement leg must not take the bench line down
+                eager[name] = {"error": repr(e)[:200]}
+    eager["what"] = ("oracle restatement of convnext.py:287-331 (F.conv1d DFT, matmul mel, F.conv2d, F.layer_norm, F.linear, "
+                     "F.gelu) run eagerly on cuda: cuDNN / cuBLAS kernels, NCHW<->NHWC permutes as in the reference; "
+                     f"allow_tf32 matmul={torch.backends.cuda.matmul.allow_tf32} cudnn={torch.backends.cudnn.allow_tf32}")
+    out["gpu_eager_baseline"] = eager
+    torch.cuda.empty_cache()
+    return out
+
+
+def extras_multi_gpu(model, eng, device, world, dist):
+    """BASELINE.json configs[3]: forward_frame_embeddings on 128 clips per GPU (1024 at 8 GPUs) + all-gather of the
+    768 x 31 x 7 outputs (85 MB per rank), serial and overlapped (chunk i's all-gather on a side stream under chunk
+    i+1's kernels).  Device-timed, max over ranks."""
+    per = 128
+    g = torch.Generator(device=device).manual_seed(99 + dist.get_rank())
+    w = (torch.randn(per, CLIP_SAMPLES, device=device, generator=g) * 0.1).clamp_(-1.0, 1.0)
+    gathered = torch.empty(world * per, 768, 31, 7, device=device)
+    side = torch.cuda.Stream(device=device)
+
+    def compute_only():
+        return eng.run(w, want=("frame",))["frame"]
+
+    def serial():
+        f = eng.run(w, want=("frame",))["frame"]
+        dist.all_gather_into_tensor(gathered, f)
+
+    chunks = [w[i:i + 64] for i in range(0, per, 64)]
+    gath_c = [torch.empty(world * 64, 768, 31, 7, device=device) for _ in chunks]
+
+    def overlapped():
+        evs = []
+        for c, gc in zip(chunks, gath_c):
+            f = eng.run(c, want=("frame",))["frame"]
+            ev = torch.cuda.Event()
+            ev.record()
+            with torch.cuda.stream(side):
+                side.wait_event(ev)
+                f.record_stream(side)
+                dist.all_gather_into_tensor(gc, f)
+            evs.append(f)
+        torch.cuda.current_stream(device).wait_stream(side)
+
+    def gather_only():
+        dist.all_gather_into_tensor(gathered, frame)
+
+    res = {}
+    frame = compute_only()
+    for name, fn in (("compute_only", compute_only), ("all_gather_only", gather_only), ("serial", serial),
+                     ("overlapped", overlapped)):
+        for _ in range(2):
+            fn()
+        dist.barrier()
+        ms = torch.tensor([_time_ms(fn, 5, device)], device=device)
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        res[name + "_ms"] = round(ms.item(), 3)
+    bytes_rank = per * 768 * 31 * 7 * 4
+    res.update({"workload": f"forward_frame_embeddings, {per} clips per GPU ({world * per} clips), all_gather_into_tensor of "
+                            "(128, 768, 31, 7) fp32 per rank (BASELINE.json configs[3])",
+                "bytes_per_rank": bytes_rank, "clips_per_s_serial": round(world * per / (res["serial_ms"] * 1e-3), 1),
+                "clips_per_s_overlapped": round(world * per / (res["overlapped_ms"] * 1e-3), 1),
+                "all_gather_busbw_gbs": round(bytes_rank * (world - 1) / (res["all_gather_only_ms"] * 1e-3) / 1e9, 1)})
+    return res
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -153,6 +300,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the configs[0]/[2]/[3]/[4] and eager-GPU legs")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -243,6 +391,12 @@ def main():
     assert len(res) == n_e2e and res[0]["probs"].shape == (BATCH, 527)
     e2e_value = world * BATCH * n_e2e / dt.item()
     clocks.__exit__()
+    extras = {}
+    if not args.no_extras:
+        if world > 1:
+            extras["frame_allgather"] = extras_multi_gpu(model, eng, device, world, dist)
+        elif rank == 0:
+            extras = extras_single_gpu(model, eng, device, _peaks())
 
     if rank == 0:
         peaks = _peaks()
@@ -298,6 +452,7 @@ def main():
                                  "FP32 pipe (~37% of the HBM figure at 100% FMA issue), see DESIGN.md"},
             "roofline_all": all_kernels,
         }
+        res.update(extras)
         if not args.no_cpu_baseline and world == 1:
             threads = os.cpu_count() or 1
             # bounded sample: ~10-15 s of host work (about 240 clips at the ~20 clips/s of a 16-core box)

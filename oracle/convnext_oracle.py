@@ -12,19 +12,33 @@ tests/golden/ that oracle/make_golden.py produced from that reference.
 import torch
 import torch.nn.functional as F
 
+import contextlib
+
 DEPTHS = [3, 3, 9, 3]
 DIMS = [96, 192, 384, 768]
+_DEVICE = "cpu"          # the oracle is a CPU checker; bench.py's `gpu_eager_baseline` MEASUREMENT leg alone moves it
+
+
+@contextlib.contextmanager
+def on_device(device):
+    """Run the same stock-PyTorch ops on another device (bench.py: eager cuDNN/cuBLAS comparator on the same B200)."""
+    global _DEVICE
+    old, _DEVICE = _DEVICE, device
+    try:
+        yield
+    finally:
+        _DEVICE = old
 
 
 def _c(sd, key, dtype):
-    return sd[key].detach().to("cpu", dtype)
+    return sd[key].detach().to(_DEVICE, dtype)
 
 
 def spectrogram(wave, sd, dtype=torch.float32, n_fft=1024, hop=320):
     """TL STFT.forward + Spectrogram.forward (called at CX:298; ctor CX:179-187):
     reflect-pad n_fft//2, two strided conv1d (windowed DFT real / imag), re^2 + im^2.
     wave (B, L) -> power (B, T, 513), T = L // hop + 1."""
-    x = wave.to("cpu", dtype)[:, None, :]
+    x = wave.to(_DEVICE, dtype)[:, None, :]
     x = F.pad(x, (n_fft // 2, n_fft // 2), mode="reflect")
     real = F.conv1d(x, _c(sd, "spectrogram_extractor.stft.conv_real.weight", dtype), stride=hop)
     imag = F.conv1d(x, _c(sd, "spectrogram_extractor.stft.conv_imag.weight", dtype), stride=hop)

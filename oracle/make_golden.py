@@ -54,9 +54,34 @@ def run_reference(model, wave):
     return out["clipwise_logits"], out["clipwise_output"], scene, frame, x[:, 0]
 
 
+def stock_head_fixture(model):
+    """parity_stock_head.npz: gamma ~ U(0.1, 0.6) trunk + the reference's own head width (std 0.02) -- the state
+    dict the north_star tolerances are asserted on as written (no scaling): demo clip, noise and tones."""
+    sd = weights.make_state_dict("parity_stock_head", PARITY_SEED)
+    model.load_state_dict(sd, strict=True)
+    model.eval()
+    pcm = read_wav_int16(os.path.join(REFERENCE_ROOT, "audio_samples", "f62-S-v2swA_200000_210000.wav"))
+    waves = {"demo": torch.from_numpy(pcm.astype(np.float32) / 32768.0)[None],
+             "noise": weights.make_waveforms(2, kind="noise", seed=0),
+             "tones": weights.make_waveforms(2, kind="tones", seed=0)}
+    out = {"parity_seed": np.array(PARITY_SEED),
+           "cks/head_audioset.weight": checksums(sd)["head_audioset.weight"],
+           "cks/stages.3.2.gamma": checksums(sd)["stages.3.2.gamma"]}
+    for name, wave in waves.items():
+        logits, probs, scene, frame, lm = run_reference(model, wave)
+        out[f"{name}/logits"] = logits.numpy()
+        out[f"{name}/probs"] = probs.numpy()
+        out[f"{name}/scene"] = scene.numpy()
+        print("stock head", name, "logits std", float(logits.std()), "range", float(logits.min()), float(logits.max()))
+    np.savez_compressed(os.path.join(GOLDEN, "parity_stock_head.npz"), **out)
+
+
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
+    if "--stock-head-only" in sys.argv:      # adds the round-2 fixture without rewriting the round-1 ones
+        stock_head_fixture(build_reference_tiny())
+        return
     sd = weights.make_state_dict("parity", PARITY_SEED)
     model = build_reference_tiny()
     model.load_state_dict(sd, strict=True)
@@ -104,6 +129,7 @@ def main():
     wave = weights.make_waveforms(1, kind="noise", seed=0)
     logits, probs, scene, frame, lm = run_reference(model, wave)
     np.savez_compressed(os.path.join(GOLDEN, "synth_init.npz"), logits=logits.numpy(), scene=scene.numpy())
+    stock_head_fixture(model)
     for f in sorted(os.listdir(GOLDEN)):
         print(f, os.path.getsize(os.path.join(GOLDEN, f)))
 

@@ -13,6 +13,11 @@ instead of torch's RNG so that the very same numbers are regenerated on any box.
                    bn0 running stats (mean -20, var 400 -- typical log-mel dB statistics),
                    biases ~ N(0, 0.02^2); with gamma = 1e-6 every Block is numerically the
                    identity and the MLP kernels would go untested.
+ * kind="parity_stock_head" : "parity" with the classifier head left at the reference's own
+                   init width (std 0.02 instead of the 3x wider, label-discriminative head of
+                   "parity"; same random stream, so every other tensor is identical).  This
+                   is the state dict the north_star tolerances (logits 2e-2 bf16 / 1e-4 fp32)
+                   are asserted on UNSCALED.
 """
 import numpy as np
 import torch
@@ -68,7 +73,10 @@ def _key_shapes():
 
 def make_state_dict(kind="parity", seed=1):
     """Full 190-key state dict (float32, + int64 num_batches_tracked)."""
-    assert kind in ("init", "parity")
+    assert kind in ("init", "parity", "parity_stock_head")
+    stock_head = kind == "parity_stock_head"
+    if stock_head:
+        kind = "parity"
     rng = np.random.default_rng(seed)
     conv_real, conv_imag, melW = frontend_constants()
     sd = {
@@ -90,7 +98,7 @@ def make_state_dict(kind="parity", seed=1):
         if is_matrix:
             # parity head: wider weights + negative bias so the 0.25-thresholded label set is
             # sparse and discriminative like a trained tagger's (demo_convnext.py:87-92)
-            t = normal(shape, 0.06 if (kind == "parity" and key == "head_audioset.weight") else 0.02)
+            t = normal(shape, 0.06 if (kind == "parity" and not stock_head and key == "head_audioset.weight") else 0.02)
         elif key == "bn0.running_mean":
             t = torch.zeros(shape) if kind == "init" else normal(shape, 3.0) - 20.0
         elif key == "bn0.running_var":

@@ -13,7 +13,7 @@
 #include <vector>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
-#define ACX_MBAR_SPIN_LIMIT 400000000u
+#define ACX_MBAR_TIMEOUT_NS 60000000000ull
 #include "ptx.cuh"
 using namespace acx;
 

@@ -10,7 +10,7 @@
 #include <cstdlib>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
-#define ACX_MBAR_SPIN_LIMIT 100000000u
+#define ACX_MBAR_TIMEOUT_NS 60000000000ull
 #include "ptx.cuh"
 using namespace acx;
 
