@@ -159,8 +159,12 @@ class Engine:
         # which implementation of the two fusable pieces to run (both are libacx kernels)
         self.frontend = frontend or os.environ.get("ACX_FRONTEND", "fused" if precision == "bf16" else "simt")
         self.mlp = mlp or os.environ.get("ACX_MLP", "fused")
+        # depthwise 7x7: "tc" = banded-Toeplitz tcgen05 GEMMs (dwconv_tc.cu) + LayerNorm pass, "simt" = CUDA-core kernel
+        # with the LayerNorm fused; ACX_DWCONV_TC_STAGES picks the stages that take the tensor-core route
+        self.dwconv = os.environ.get("ACX_DWCONV", "tc" if precision == "bf16" else "simt")
+        self.dwconv_tc_stages = tuple(int(c) for c in os.environ.get("ACX_DWCONV_TC_STAGES", "012"))
         if precision == "fp32":
-            self.frontend, self.mlp = "simt", "gemm"
+            self.frontend, self.mlp, self.dwconv = "simt", "gemm", "simt"
         # LRU of workspaces keyed by (clips, samples); each owns the CUDA graphs captured over its buffers, so a
         # variable-length extraction or a ragged last batch neither re-allocates nor re-captures per call
         self._ws = collections.OrderedDict()
@@ -252,6 +256,10 @@ class Engine:
             C = int(tag[len("mlp_fused_c"):])
             s = DIMS.index(C)
             return "tensor", 2.0 * (n * hs[s] * (56 >> s)) * C * 4 * C * 2
+        if tag.startswith(("dwconv_tc_c", "ln_rows_c")):
+            C = int(tag.rsplit("_c", 1)[1])
+            s = DIMS.index(C)
+            return "hbm", 2.0 * n * hs[s] * (56 >> s) * C * es
         if tag.startswith("dwconv_ln_c"):
             C = int(tag[len("dwconv_ln_c"):])
             s = DIMS.index(C)
@@ -315,8 +323,12 @@ class Engine:
             C, H = DIMS[s], ws["hs"][s]
             M = n * H * Wd
             for blk in w.blocks[s]:
-                self._call(f"dwconv_ln_c{C}", "acx_dwconv_ln", x, blk["dw_w"].data_ptr(), blk["dw_b"].data_ptr(), blk["ln_w"].data_ptr(),
-                       blk["ln_b"].data_ptr(), y, n, H, Wd, C, self.adt, st)
+                if self.dwconv == "tc" and s in self.dwconv_tc_stages:
+                    self._call(f"dwconv_tc_c{C}", "acx_dwconv_tc", x, blk["dw_w"].data_ptr(), blk["dw_b"].data_ptr(), y, n, H, Wd, C, st)
+                    self._call(f"ln_rows_c{C}", "acx_layernorm_rows", y, blk["ln_w"].data_ptr(), blk["ln_b"].data_ptr(), y, M, C, st)
+                else:
+                    self._call(f"dwconv_ln_c{C}", "acx_dwconv_ln", x, blk["dw_w"].data_ptr(), blk["dw_b"].data_ptr(), blk["ln_w"].data_ptr(),
+                               blk["ln_b"].data_ptr(), y, n, H, Wd, C, self.adt, st)
                 if self.mlp == "fused" and C in (96, 192):
                     self._call(f"mlp_fused_c{C}", "acx_mlp_fused", y, x, blk["w1"].data_ptr(), blk["b1"].data_ptr(), blk["w2"].data_ptr(),
                            blk["b2"].data_ptr(), blk["gamma"].data_ptr(), M, C, st)

@@ -96,6 +96,16 @@ ACX_API int acx_stem(const float* logmel, const float* w, const float* bias, con
 ACX_API int acx_dwconv_ln(const void* x, const void* w, const float* bias, const float* ln_w, const float* ln_b,
                   void* y, int B, int H, int W, int C, int act_dtype, void* stream);
 
+/* ---- Block part 1 on the tensor cores (bf16 mode): depthwise 7x7 (pad 3) + bias (CX:76) as banded-Toeplitz
+ *      tcgen05 GEMMs, then the channels-last LayerNorm (CX:78) as its own pass. -------------------------------- */
+/* x (B,H,W,C) bf16 -> v (B,H,W,C) bf16 = conv + bias, NOT normalised; w (49, C) bf16; W in {56,28,14,7}, C % 8 == 0;
+ * out of place. */
+ACX_API int acx_dwconv_tc(const void* x, const void* w, const float* bias, void* v, int B, int H, int W, int C,
+                  void* stream);
+/* rows of C bf16 values: out = LayerNorm(in) * ln_w + ln_b, eps 1e-6, fp32 statistics; in == out allowed. */
+ACX_API int acx_layernorm_rows(const void* in, const float* ln_w, const float* ln_b, void* out, long long M, int C,
+                       void* stream);
+
 /* ---- downsample prologue: channels_first LayerNorm + 2x2/s2 patch gather (CX:231-234) ------- */
 /* x (B,H,W,C) -> a (B*(H/2)*(W/2), 4C) with k = (dy*2+dx)*C + c  (the GEMM A operand). */
 ACX_API int acx_ln_patchify(const void* x, const float* ln_w, const float* ln_b, void* a, int B, int H, int W, int C,

@@ -150,6 +150,40 @@ def test_dwconv_ln(sd, stage, H, dtype):
     assert err < (2e-4 if dtype == torch.float32 else 4e-2), err
 
 
+@pytest.mark.parametrize("stage,H,B", [(0, 13, 2), (0, 252, 3), (0, 130, 2), (1, 126, 2), (1, 9, 3), (2, 63, 3), (2, 64, 2),
+                                       (3, 31, 2), (3, 5, 1)])
+def test_dwconv_tc_then_layernorm_rows(sd, stage, H, B):
+    """Tensor-core depthwise 7x7 (banded-Toeplitz tcgen05 GEMMs, acx_dwconv_tc) + acx_layernorm_rows against the
+    oracle's F.conv2d / F.layer_norm (CX:76-78): full 10 s heights, heights that are not multiples of the 63-row tile,
+    images shorter than the halo, every stage width.  The conv output is compared BEFORE the LayerNorm too: it is
+    exact up to the bf16 rounding of the result (bf16 x bf16 products accumulate in fp32 in TMEM)."""
+    C, Wd = O.DIMS[stage], 56 >> stage
+    p = f"stages.{stage}.1."
+    g = torch.Generator().manual_seed(stage * 1000 + H)
+    xq = (torch.randn(B, H, Wd, C, generator=g) * 1.5).to(torch.bfloat16)
+    wq = sd[p + "dwconv.weight"].to(torch.bfloat16)
+    conv = F.conv2d(xq.float().permute(0, 3, 1, 2), wq.float(), sd[p + "dwconv.bias"], padding=3, groups=C)
+    conv = conv.permute(0, 2, 3, 1).contiguous()
+    ref = F.layer_norm(conv, (C,), sd[p + "norm.weight"], sd[p + "norm.bias"], 1e-6)
+    w = wq.reshape(C, 49).t().contiguous().to(DEV)
+    b, lw, lb = (sd[p + k].to(DEV) for k in ("dwconv.bias", "norm.weight", "norm.bias"))
+    xd = xq.to(DEV)
+    v = torch.full((B, H, Wd, C), float("nan"), device=DEV, dtype=torch.bfloat16)
+    N.call("acx_dwconv_tc", xd.data_ptr(), w.data_ptr(), b.data_ptr(), v.data_ptr(), B, H, Wd, C, _st())
+    torch.cuda.synchronize()
+    vf = v.float().cpu()
+    assert torch.isfinite(vf).all(), "unwritten outputs"
+    ulp = torch.maximum(conv.abs(), torch.tensor(2.0 ** -126)) * 2.0 ** -8
+    assert ((vf - conv).abs() <= 0.51 * ulp + 1e-6).all(), (vf - conv).abs().max().item()
+    y = torch.empty_like(v)
+    N.call("acx_layernorm_rows", v.data_ptr(), lw.data_ptr(), lb.data_ptr(), y.data_ptr(), B * H * Wd, C, _st())
+    err = (y.float().cpu() - ref).abs().max().item()
+    assert err < 4e-2, err
+    # in place
+    N.call("acx_layernorm_rows", v.data_ptr(), lw.data_ptr(), lb.data_ptr(), v.data_ptr(), B * H * Wd, C, _st())
+    assert torch.equal(v, y)
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("stage,H", [(0, 10), (1, 7), (2, 63)])
 def test_ln_patchify_then_gemm_is_downsample(sd, stage, H, dtype):

@@ -181,3 +181,49 @@ def test_checkpoint_converter_round_trip(tmp_path):
     assert all(torch.equal(back[k], sd[k]) for k in sd)
     m = acx.ConvNeXt.from_pretrained(str(dst))
     assert all(torch.equal(v, sd[k]) for k, v in m.state_dict().items())
+
+
+def test_reference_import_path_alias():
+    """The reference's scripts import `audioset_convnext_inf.pytorch.convnext` (demo_convnext.py:13,
+    evaluate_convnext_on_audioset.py:14, pytorch/extract_embeddings.py:12) and `pytorch_utils` (PU:9-15, 63-137): both
+    resolve to the B200 package, so those scripts run unmodified against libacx."""
+    from audioset_convnext_inf.pytorch.convnext import ConvNeXt, convnext_tiny
+    from audioset_convnext_inf.pytorch import pytorch_utils
+    assert ConvNeXt is acx.ConvNeXt and convnext_tiny is acx.convnext_tiny
+    assert pytorch_utils.forward is acx.evalloop.forward
+    import numpy as np
+    assert pytorch_utils.move_data_to_device(np.zeros(3, np.float32), "cpu").dtype == torch.float32
+    assert pytorch_utils.move_data_to_device(np.zeros(3, np.int64), "cpu").dtype == torch.int64
+    obj = np.empty(2, dtype=object)
+    assert pytorch_utils.move_data_to_device(obj, "cpu") is obj          # PU:13-14: returned unchanged
+
+
+def test_checkpoint_format_is_not_sniffed_from_leading_bytes(tmp_path):
+    """A safetensors header length is an arbitrary u64: low byte 0x80 (pickle opcode) or 'PK' (zip magic) must not send
+    the file to torch.load.  Metadata padding is used to force both header lengths."""
+    import json
+    import struct
+    from safetensors.torch import save_file
+    sd = {k: v.contiguous() for k, v in weights.make_state_dict("parity", 3).items()}
+    for want_low, name in ((b"\x80", "a.safetensors"), (b"PK", "b.safetensors"), (b"PK", "noext")):
+        p = str(tmp_path / name)
+        save_file(sd, p)
+        raw = open(p, "rb").read()
+        (n,) = struct.unpack("<Q", raw[:8])
+        header, body = json.loads(raw[8:8 + n]), raw[8 + n:]
+        target = n + 64
+        while struct.pack("<Q", target)[:len(want_low)] != want_low:
+            target += 1
+        for pad in range(0, 1 << 17):               # pad the metadata until the serialised header has that length
+            header["__metadata__"] = {"pad": "x" * pad}
+            hb = json.dumps(header, separators=(",", ":")).encode()
+            if len(hb) == target:
+                break
+            if len(hb) > target:
+                target += 1 << (8 * len(want_low))
+        assert len(hb) == target
+        with open(p, "wb") as fh:
+            fh.write(struct.pack("<Q", len(hb)) + hb + body)
+        assert open(p, "rb").read(len(want_low)) == want_low
+        m = acx.ConvNeXt.from_pretrained(p)
+        assert torch.equal(m.state_dict()["stages.2.4.dwconv.weight"], sd["stages.2.4.dwconv.weight"])

@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(128) timing(long long* cyc, int reps) {
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem = *slot;
-  if (tid == 0) {
+  if (warp == 1 && ptx::elect_one()) {
     const uint64_t da = ptx::umma_desc_sw128_kmajor(ptx::smem_u32(sA));
     const uint64_t db = ptx::umma_desc_sw64_kmajor(ptx::smem_u32(sB));
     constexpr uint32_t idesc = ptx::umma_idesc_bf16(M, N);
