@@ -25,13 +25,19 @@ SIGNATURES = {
     "acx_power_mel_log": [_vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp],
     "acx_frontend_fused": [_vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     "acx_stem": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
+    "acx_stem_gp": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp],
     "acx_dwconv_ln": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     "acx_dwconv_tc": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "acx_layernorm_rows": [_vp, _vp, _vp, _vp, _ll, _i, _vp],
+    "acx_dwconv_tc_gp": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
+    "acx_gp_transpose": [_vp, _vp, _ll, _i, _i, _vp],
+    "acx_ln_patchify_gp": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "acx_ln_patchify": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     "acx_gemm_bf16": [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp],
     "acx_gemm_f32": [_vp, _ll, _i, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp],
     "acx_mlp_fused": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp],
+    "acx_mlp_fused_ln": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp],
+    "acx_mlp_fused_gp": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp],
     "acx_head": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
     "acx_nhwc_to_nchw_f32": [_vp, _vp, _i, _i, _i, _i, _i, _vp],
     "acx_resample_fit": [_vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],

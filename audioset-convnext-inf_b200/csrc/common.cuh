@@ -139,8 +139,17 @@ __device__ __forceinline__ void gelu_op_tanh(GeluPair& g) {
 // stage T on t[0..4) (if kT) interleaved with stage A on a[0..4) (if kA): acc = 8 fp32 accumulator words, sbias_addr =
 // shared-space address of their 8 biases.  (Fetching the biases a whole step ahead into 8 more registers was tried:
 // the kernel sits at the 128-register cap and got 5 % slower.)
-template <bool kT, bool kA>
-__device__ __forceinline__ void gelu_stage_ta4(GeluPair* t, GeluPair* a, const uint32_t* acc, uint32_t sbias_addr) {
+// kFold: the accumulator is G = v . (W1 diag(ln_w))^T of the UN-normalised conv output v, and the LayerNorm (CX:78) is
+// applied here as a rank-1 correction:  pre = rstd_p * G + (nmr_p * s_j + b1'_j)   with  nmr_p = -mean_p * rstd_p,
+// s_j = sum_c W1'[j, c],  b1' = b1 + W1 ln_b   (fold = {rstd, rstd}, {nmr, nmr} packed; s sits `s_off` bytes behind
+// the biases in shared memory).  One extra packed FMA per column pair instead of a LayerNorm pass over the tensor.
+struct LnFold {
+  unsigned long long rstd2, nmr2;
+  uint32_t s_off;
+};
+template <bool kT, bool kA, bool kFold = false>
+__device__ __forceinline__ void gelu_stage_ta4(GeluPair* t, GeluPair* a, const uint32_t* acc, uint32_t sbias_addr,
+                                               const LnFold fold = LnFold{}) {
   const unsigned long long k50 = f2_pack(50.0f, 50.0f);
   const unsigned long long kc = f2_pack(-3.51516788e-04f, -3.51516788e-04f);
   const unsigned long long kb = f2_pack(3.70056460e-02f, 3.70056460e-02f);
@@ -152,9 +161,19 @@ __device__ __forceinline__ void gelu_stage_ta4(GeluPair* t, GeluPair* a, const u
     for (int i = 0; i < 4; ++i) {
       float2 b;
       asm("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(b.x), "=f"(b.y) : "r"(sbias_addr + 8 * i));
-      asm volatile("add.rn.f32x2 %0, %1, %2;"
-                   : "=l"(a[i].x)
-                   : "l"(f2_pack(__uint_as_float(acc[2 * i]), __uint_as_float(acc[2 * i + 1]))), "l"(f2_pack(b.x, b.y)));
+      if (kFold) {
+        float2 sj;
+        asm("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(sj.x), "=f"(sj.y) : "r"(sbias_addr + fold.s_off + 8 * i));
+        unsigned long long tt;
+        asm volatile("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(tt) : "l"(fold.nmr2), "l"(f2_pack(sj.x, sj.y)), "l"(f2_pack(b.x, b.y)));
+        asm volatile("fma.rn.f32x2 %0, %1, %2, %3;"
+                     : "=l"(a[i].x)
+                     : "l"(fold.rstd2), "l"(f2_pack(__uint_as_float(acc[2 * i]), __uint_as_float(acc[2 * i + 1]))), "l"(tt));
+      } else {
+        asm volatile("add.rn.f32x2 %0, %1, %2;"
+                     : "=l"(a[i].x)
+                     : "l"(f2_pack(__uint_as_float(acc[2 * i]), __uint_as_float(acc[2 * i + 1]))), "l"(f2_pack(b.x, b.y)));
+      }
     }
   }
   if (kT) gelu_op_tanh(t[1]);
@@ -196,15 +215,16 @@ __device__ __forceinline__ void gelu_stage_c8_twice_bf16(const GeluPair* g, uint
 
 // Drop-in for bias_gelu_tile<16, kTwice> built from the stages above: T of pairs [4k, 4k+4) is interleaved with A of
 // pairs [4k+4, 4k+8), so each warp's instruction stream mixes XU and FMA work instead of alternating long phases.
-template <bool kTwice>
+template <bool kTwice, bool kFold = false>
 __device__ __forceinline__ void bias_gelu_tile16_sp(const uint32_t* __restrict__ acc /*[32] fp32 bits*/,
-                                                    const float* __restrict__ sbias /*smem*/, float2 (&out)[16]) {
+                                                    const float* __restrict__ sbias /*smem*/, float2 (&out)[16],
+                                                    const LnFold fold = LnFold{}) {
   GeluPair g[16];
   const uint32_t sb = static_cast<uint32_t>(__cvta_generic_to_shared(sbias));
-  gelu_stage_ta4<false, true>(nullptr, g, acc, sb);
-  gelu_stage_ta4<true, true>(g, g + 4, acc + 8, sb + 32);
-  gelu_stage_ta4<true, true>(g + 4, g + 8, acc + 16, sb + 64);
-  gelu_stage_ta4<true, true>(g + 8, g + 12, acc + 24, sb + 96);
+  gelu_stage_ta4<false, true, kFold>(nullptr, g, acc, sb, fold);
+  gelu_stage_ta4<true, true, kFold>(g, g + 4, acc + 8, sb + 32, fold);
+  gelu_stage_ta4<true, true, kFold>(g + 4, g + 8, acc + 16, sb + 64, fold);
+  gelu_stage_ta4<true, true, kFold>(g + 8, g + 12, acc + 24, sb + 96, fold);
   gelu_stage_ta4<true, false>(g + 12, nullptr, nullptr, 0);
   const unsigned long long khalf = f2_pack(0.5f, 0.5f);
 #pragma unroll

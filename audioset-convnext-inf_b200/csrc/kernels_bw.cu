@@ -444,7 +444,9 @@ __global__ void __launch_bounds__(S* C / 2, dw_min_blocks(S* C / 2))
 // of a warp moves 512 contiguous-per-pixel bytes, statistics are reduced with log2(C/24) shuffles, and each lane
 // works on NPIX pixels at once so their loads overlap.  (First version: 4-byte loads, 28 % of HBM roofline.)
 // =============================================================================================
-template <typename T, int C>
+// GP: x is group-planar [C/8][B*H*W][8] (bf16 only; the residual stream of the stages whose depthwise conv runs on the
+// tensor cores); the patch matrix `a` is row-major either way.
+template <typename T, int C, bool GP = false>
 __global__ void __launch_bounds__(256, 3)
     ln_patchify_kernel(const T* __restrict__ x, const float* __restrict__ ln_w, const float* __restrict__ ln_b,
                        T* __restrict__ a, int B, int H, int W) {
@@ -473,12 +475,14 @@ __global__ void __launch_bounds__(256, 3)
     const int wi = (int)(pp % (Wo * 2));
     const int hi = (int)((pp / (Wo * 2)) % (Ho * 2));
     const int b = (int)(pp / ((long long)Wo * 2 * Ho * 2));
-    const T* src = x + (((size_t)b * H + hi) * W + wi) * C + lig * CH;
+    const size_t pix_in = ((size_t)b * H + hi) * W + wi;
+    const size_t gp_stride = ((size_t)B * H * W + 127) / 128 * 128;     // plane stride in 16-byte vectors (rows padded to 128)
+    const T* src = GP ? x + ((size_t)(lig * NV) * gp_stride + pix_in) * VE : x + pix_in * C + lig * CH;
     const size_t m = ((size_t)b * Ho + (hi >> 1)) * Wo + (wi >> 1);
     dst_off[q] = m * (size_t)(4 * C) + (size_t)((hi & 1) * 2 + (wi & 1)) * C + lig * CH;
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
-      const uint4 raw = __ldg(reinterpret_cast<const uint4*>(src) + j);
+      const uint4 raw = __ldg(reinterpret_cast<const uint4*>(src) + (GP ? j * gp_stride : (size_t)j));
       if (sizeof(T) == 2) {
         float2 f;
         f = Pair<bf16>::unpack(raw.x); v[q][8 * j + 0] = f.x; v[q][8 * j + 1] = f.y;
@@ -762,7 +766,7 @@ static int dispatch_dwconv(const void* x, const void* w, const float* bias, cons
 
 namespace acx {
 int launch_stem_umma(const float* logmel, const float* w, const float* bias, const float* ln_w, const float* ln_b,
-                     void* out, int B, int T, int n_mels, cudaStream_t st);   // stem_umma.cu
+                     void* out, int B, int T, int n_mels, int gp, cudaStream_t st);   // stem_umma.cu
 }
 using namespace acx;
 
@@ -820,7 +824,7 @@ int acx_stem(const float* logmel, const float* w, const float* bias, const float
   // bf16 mode: tensor-core stem (stem_umma.cu); ACX_STEM=simt selects the CUDA-core kernel for A/B timing
   static const bool stem_simt = [] { const char* e = getenv("ACX_STEM"); return e && e[0] == 's'; }();
   if (act_dtype == ACX_BF16 && !stem_simt)
-    return launch_stem_umma(logmel, w, bias, ln_w, ln_b, out, B, T, n_mels, st);
+    return launch_stem_umma(logmel, w, bias, ln_w, ln_b, out, B, T, n_mels, 0, st);
   if (act_dtype == ACX_BF16) {
     const int smem = 19 * 96 * 4 + 4 * 32 * (96 * 2 + 16);
     stem_kernel<bf16><<<blocks, 128, smem, st>>>(logmel, w, bias, ln_w, ln_b, reinterpret_cast<bf16*>(out), B, T,
@@ -845,6 +849,14 @@ int acx_dwconv_ln(const void* x, const void* w, const float* bias, const float* 
                                : dispatch_dwconv<float>(x, w, bias, ln_w, ln_b, y, B, H, W, C, st);
 }
 
+// bf16 tensor-core stem writing the group-planar layout [12][Mp][8] directly (Mp = B * H0 * 56 rounded up to 128)
+int acx_stem_gp(const float* logmel, const float* w, const float* bias, const float* ln_w, const float* ln_b, void* out,
+                int B, int T, int n_mels, void* stream) {
+  ACX_CHECK(logmel && w && bias && ln_w && ln_b && out, ACX_ERR_ARG, "stem_gp: null pointer");
+  ACX_CHECK(n_mels % 4 == 0 && B > 0 && T > 0, ACX_ERR_ARG, "stem_gp: n_mels must be a multiple of 4");
+  return launch_stem_umma(logmel, w, bias, ln_w, ln_b, out, B, T, n_mels, 1, reinterpret_cast<cudaStream_t>(stream));
+}
+
 int acx_ln_patchify(const void* x, const float* ln_w, const float* ln_b, void* a, int B, int H, int W, int C,
                     int act_dtype, void* stream) {
   ACX_CHECK(x && ln_w && ln_b && a, ACX_ERR_ARG, "ln_patchify: null pointer");
@@ -863,6 +875,26 @@ int acx_ln_patchify(const void* x, const float* ln_w, const float* ln_b, void* a
     if (C == 96) ACX_LNP(float, 96); else if (C == 192) ACX_LNP(float, 192); else ACX_LNP(float, 384);
   }
 #undef ACX_LNP
+  ACX_CUDA(cudaGetLastError());
+  return ACX_OK;
+}
+
+// Same with a group-planar input x = [C/8][B*H*W][8] bf16 (stages 0 / 1 behind the tensor-core depthwise conv).
+int acx_ln_patchify_gp(const void* x, const float* ln_w, const float* ln_b, void* a, int B, int H, int W, int C,
+                       void* stream) {
+  ACX_CHECK(x && ln_w && ln_b && a, ACX_ERR_ARG, "ln_patchify_gp: null pointer");
+  ACX_CHECK((C == 96 || C == 192) && H >= 2 && W >= 2, ACX_ERR_ARG,
+            "ln_patchify_gp: unsupported shape C=%d H=%d W=%d (C must be 96 or 192)", C, H, W);
+  const long long total = (long long)B * (H / 2) * 2 * (W / 2) * 2;
+  const long long lanes = (total + 1) / 2 * (C / 24);
+  const int blocks = (int)((lanes + 255) / 256);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (C == 96)
+    ln_patchify_kernel<bf16, 96, true><<<blocks, 256, 0, st>>>(reinterpret_cast<const bf16*>(x), ln_w, ln_b,
+                                                               reinterpret_cast<bf16*>(a), B, H, W);
+  else
+    ln_patchify_kernel<bf16, 192, true><<<blocks, 256, 0, st>>>(reinterpret_cast<const bf16*>(x), ln_w, ln_b,
+                                                                reinterpret_cast<bf16*>(a), B, H, W);
   ACX_CUDA(cudaGetLastError());
   return ACX_OK;
 }

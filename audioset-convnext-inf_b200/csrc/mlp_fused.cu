@@ -29,8 +29,89 @@ struct MlpArgs {
   const float* b2;
   const float* gamma;
   int M;
+  const float* ln_w;  // optional: channels-last LayerNorm (convnext.py:78) applied to the y tile IN SHARED MEMORY before
+  const float* ln_b;  // GEMM1 reads it -- y then holds the raw depthwise-conv output (acx_dwconv_tc); nullptr = y is final
+  const float* ln_s;  // FOLD mode: s_j = sum_c W1'[j, c] of the LayerNorm-folded weights W1' = W1 diag(ln_w) (w1 / b1 then
+                      // ARE W1' and b1 + W1 ln_b): the kernel only computes per-row statistics of the y tile and applies
+                      // the LayerNorm as a rank-1 correction in the GELU epilogue (common.cuh, LnFold)
   unsigned long long* trace;   // optional [16 tiles][2 roles][32 events] SM-clock stamps of CTA 0 (tools/trace_mlp.py)
 };
+
+// LayerNorm of one 128-row operand tile in place in shared memory: thread = row, `chunk(j)` = address of the row's j-th
+// 16-byte piece (8 channels, already de-swizzled by the caller).  Two sweeps over the row: shifted single-pass statistics
+// (shift = the row's first channel, so  E[d^2] - E[d]^2  does not cancel for rows with a large common offset), then
+// out = x * (rstd w) + (b - mean rstd w).  fp32 statistics, eps 1e-6, result rounded to bf16 -- the same arithmetic as
+// acx_layernorm_rows up to the summation order.  Costs ~8 instructions per channel on the 4 epilogue-2 warps and saves
+// the separate LayerNorm pass over HBM (2 x M x C x 2 B).
+template <int C, typename ChunkFn>
+__device__ __forceinline__ void ln_row_in_smem(ChunkFn chunk, const float* __restrict__ sw, const float* __restrict__ sb) {
+  constexpr int NCH = C / 8;
+  float shift;
+  {
+    const uint32_t w0 = *reinterpret_cast<const uint32_t*>(chunk(0));
+    shift = __uint_as_float(w0 << 16);
+  }
+  const float2 sh2 = make_float2(-shift, -shift);
+  float2 s = make_float2(0.f, 0.f), q = make_float2(0.f, 0.f);
+#pragma unroll 4
+  for (int j = 0; j < NCH; ++j) {
+    const uint4 v = *reinterpret_cast<const uint4*>(chunk(j));
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 d = __fadd2_rn(Pair<bf16>::unpack(w[k]), sh2);
+      s = __fadd2_rn(s, d);
+      q = __ffma2_rn(d, d, q);
+    }
+  }
+  const float md = (s.x + s.y) * (1.0f / C);                       // mean of the shifted values
+  const float var = fmaxf((q.x + q.y) * (1.0f / C) - md * md, 0.f);
+  const float rstd = rsqrtf(var + 1e-6f);
+  const float nmr = -(md + shift) * rstd;                          // -mean * rstd
+  const float2 r2 = make_float2(rstd, rstd), n2 = make_float2(nmr, nmr);
+#pragma unroll 2
+  for (int j = 0; j < NCH; ++j) {
+    uint8_t* pc = chunk(j);
+    const uint4 v = *reinterpret_cast<const uint4*>(pc);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 g = *reinterpret_cast<const float2*>(sw + 8 * j + 2 * k);
+      const float2 b = *reinterpret_cast<const float2*>(sb + 8 * j + 2 * k);
+      const float2 t = __fmul2_rn(r2, g);
+      const float2 u = __ffma2_rn(n2, g, b);
+      const float2 y = __ffma2_rn(Pair<bf16>::unpack(w[k]), t, u);
+      o[k] = Pair<bf16>::pack(y.x, y.y);
+    }
+    *reinterpret_cast<uint4*>(pc) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// Per-row LayerNorm statistics of an operand tile in shared memory (read only): (rstd, -mean * rstd), same shifted
+// single-pass arithmetic as ln_row_in_smem.
+template <int C, typename ChunkFn>
+__device__ __forceinline__ float2 ln_row_stats_smem(ChunkFn chunk) {
+  constexpr int NCH = C / 8;
+  const float shift = __uint_as_float(*reinterpret_cast<const uint32_t*>(chunk(0)) << 16);
+  const float2 sh2 = make_float2(-shift, -shift);
+  float2 s = make_float2(0.f, 0.f), q = make_float2(0.f, 0.f);
+#pragma unroll 4
+  for (int j = 0; j < NCH; ++j) {
+    const uint4 v = *reinterpret_cast<const uint4*>(chunk(j));
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 d = __fadd2_rn(Pair<bf16>::unpack(w[k]), sh2);
+      s = __fadd2_rn(s, d);
+      q = __ffma2_rn(d, d, q);
+    }
+  }
+  const float md = (s.x + s.y) * (1.0f / C);
+  const float var = fmaxf((q.x + q.y) * (1.0f / C) - md * md, 0.f);
+  const float rstd = rsqrtf(var + 1e-6f);
+  return make_float2(rstd, -(md + shift) * rstd);
+}
 
 template <int C_>
 struct MlpCfg {
@@ -52,8 +133,8 @@ struct MlpCfg {
   static constexpr int STG_TILE = 32 * 64;            // 32 rows x 32 bf16, SWIZZLE_64B
   static constexpr int STG_PER_WARP = STG_TILE;       // one tile: residual transpose in, output staging out
   static constexpr int OFF_BAR = OFF_STG + 8 * STG_PER_WARP;
-  static constexpr int OFF_VEC = OFF_BAR + 512;       // b1[4C], b2[C], gamma[C] staged once per CTA
-  static constexpr int SMEM_BYTES = OFF_VEC + (HD + 2 * C) * 4 + 1024;
+  static constexpr int OFF_VEC = OFF_BAR + 512;       // b1[4C], b2[C], gamma[C], ln_w[C], ln_b[C] staged once per CTA
+  static constexpr int SMEM_BYTES = OFF_VEC + (2 * HD + 4 * C) * 4 + 2 * BM * 8 + 1024;   // + s[4C], row stats [2][128]
   static constexpr int D2_COL = 0, D1_COL = 256, TMEM_COLS = 512;
   static constexpr int OUT_CHUNKS = C / 32;           // 32-column output chunks: 3 / 6
   static constexpr int OUT_G0 = (OUT_CHUNKS + 1) / 2;
@@ -63,7 +144,7 @@ struct MlpCfg {
   static_assert(SMEM_BYTES <= 227 * 1024, "smem budget");
 };
 
-template <int C>
+template <int C, bool GP, bool FOLD>   // GP: group-planar y / x, FOLD: rank-1 LayerNorm; see mlp_fused96_kernel
 __global__ void __launch_bounds__(512, 1)
     mlp_fused_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmW1,
                      const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmOut, MlpArgs a) {
@@ -81,14 +162,27 @@ __global__ void __launch_bounds__(512, 1)
   uint64_t* h_empty = h_full + 2;                      // [2]
   uint64_t* d2_full = h_empty + 2;                     // [1]
   uint64_t* d2_empty = d2_full + 1;                    // [1]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d2_empty + 1);
+  uint64_t* a_ready = d2_empty + 1;                    // [A_BUFS]  y tile normalised in place (LayerNorm mode only)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_ready + Cfg::A_BUFS);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   float* sb1 = reinterpret_cast<float*>(smem + Cfg::OFF_VEC);
   float* sb2 = sb1 + Cfg::HD;
   float* sgamma = sb2 + C;
+  float* slnw = sgamma + C;
+  float* slnb = slnw + C;
+  float* ss1 = slnb + C;                                          // FOLD: s[4C]
+  float2* sstat = reinterpret_cast<float2*>(ss1 + Cfg::HD);       // FOLD: [2][128] (rstd, -mean rstd) per row
+  const bool ln = a.ln_w != nullptr;
   for (int i = threadIdx.x; i < Cfg::HD; i += blockDim.x) sb1[i] = a.b1[i];
+  if (FOLD)
+    for (int i = threadIdx.x; i < Cfg::HD; i += blockDim.x) ss1[i] = a.ln_s[i];
+  if (ln)
+    for (int i = threadIdx.x; i < C; i += blockDim.x) {
+      slnw[i] = a.ln_w[i];
+      slnb[i] = a.ln_b[i];
+    }
   for (int i = threadIdx.x; i < C; i += blockDim.x) {
     // the hidden tile holds 2 * gelu(.), so  x + gamma (0.5 acc + b2) = x + (0.5 gamma) acc + gamma b2:
     sgamma[i] = 0.5f * a.gamma[i];       // multiplies the GEMM2 accumulator
@@ -108,7 +202,8 @@ __global__ void __launch_bounds__(512, 1)
     }
     for (int s = 0; s < Cfg::A_BUFS; ++s) {
       ptx::mbar_init(&a_full[s], 1);
-      ptx::mbar_init(&a_empty[s], 1);
+      ptx::mbar_init(&a_empty[s], FOLD ? 5 : 1);          // FOLD: the 4 statistics warps read the tile too
+      ptx::mbar_init(&a_ready[s], 4);
     }
     for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(&d1_full[s], 1);
@@ -140,8 +235,12 @@ __global__ void __launch_bounds__(512, 1)
         ptx::mbar_wait(&a_empty[buf], (use & 1) ^ 1);
         uint8_t* sa = smem + Cfg::OFF_A + buf * Cfg::KB1 * Cfg::A_TILE;
         ptx::mbar_arrive_expect_tx(&a_full[buf], Cfg::KB1 * Cfg::A_TILE);
-        for (int kb = 0; kb < Cfg::KB1; ++kb)
-          ptx::tma_load_2d(sa + kb * Cfg::A_TILE, &tmY, &a_full[buf], kb * Cfg::BK, tile * Cfg::BM);
+        if (GP) {
+          ptx::tma_load_3d(sa, &tmY, &a_full[buf], 0, tile * (Cfg::BM / 32), 0);   // box {32 rows x 16 B, 4, C / 8 groups}
+        } else {
+          for (int kb = 0; kb < Cfg::KB1; ++kb)
+            ptx::tma_load_2d(sa + kb * Cfg::A_TILE, &tmY, &a_full[buf], kb * Cfg::BK, tile * Cfg::BM);
+        }
       }
     }
   } else if (warp == 0) {
@@ -219,7 +318,7 @@ __global__ void __launch_bounds__(512, 1)
           }
           ptx::umma_commit(&h_empty[hb]);
         };
-        ptx::mbar_wait(&a_full[abuf], ause & 1);
+        ptx::mbar_wait((ln && !FOLD) ? &a_ready[abuf] : &a_full[abuf], ause & 1);
         ptx::tc_fence_after();
         for (int h = 0; h < Cfg::NC; ++h, ++gc) {
           const int db1 = gc & 1;
@@ -229,11 +328,13 @@ __global__ void __launch_bounds__(512, 1)
           for (int kb = 0; kb < Cfg::KB1; ++kb) {
             ptx::mbar_wait(&ring_full[slot], phase);
             ptx::tc_fence_after();
-            const uint64_t da = ptx::umma_desc_sw128_kmajor(sa + kb * Cfg::A_TILE);
+            const uint64_t da = GP ? ptx::umma_desc_nosw_kmajor(sa + kb * Cfg::A_TILE, Cfg::BM * 16, 128)
+                                   : ptx::umma_desc_sw128_kmajor(sa + kb * Cfg::A_TILE);
             const uint64_t db = ptx::umma_desc_sw128_kmajor(ptx::smem_u32(smem + Cfg::OFF_RING + slot * Cfg::SLOT));
 #pragma unroll
             for (int k = 0; k < Cfg::BK / 16; ++k)
-              if (kb * Cfg::BK + k * 16 < C) ptx::umma_bf16(d1, da + 2 * k, db + 2 * k, idesc1, (kb | k) != 0 ? 1u : 0u);
+              if (kb * Cfg::BK + k * 16 < C)
+                ptx::umma_bf16(d1, da + (GP ? k * (4096 >> 4) : 2 * k), db + 2 * k, idesc1, (kb | k) != 0 ? 1u : 0u);
             ptx::umma_commit(&ring_empty[slot]);
             advance();
           }
@@ -254,7 +355,9 @@ __global__ void __launch_bounds__(512, 1)
     const int row_in_tile = quad * 32 + lane;
     const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
     uint32_t gc = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    LnFold fold{0ull, 0ull, ptx::smem_u32(ss1) - ptx::smem_u32(sb1)};
+    int it1 = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it1) {
       for (int h = 0; h < Cfg::NC; ++h, ++gc) {
         const int buf = gc & 1;
         const uint32_t par = (gc >> 1) & 1;
@@ -262,6 +365,13 @@ __global__ void __launch_bounds__(512, 1)
         ptx::tc_fence_after();
         const uint32_t t0 = lane_base + Cfg::D1_COL + buf * Cfg::NH + group * 64;
         const float* bias = sb1 + h * Cfg::NH + group * 64;
+        if (FOLD && h == 0) {                           // this tile's row statistics (written by the epilogue-2 warps)
+          const int abuf = it1 % Cfg::A_BUFS;
+          ptx::mbar_wait(&a_ready[abuf], (it1 / Cfg::A_BUFS) & 1);
+          const float2 stt = sstat[(it1 & 1) * Cfg::BM + row_in_tile];
+          fold.rstd2 = f2_pack(stt.x, stt.x);
+          fold.nmr2 = f2_pack(stt.y, stt.y);
+        }
         // this warp group's 64 hidden columns are k-block `group` of the hidden tile: one 128 B swizzled row per lane
         uint8_t* hrow = smem + Cfg::OFF_H + (buf * Cfg::KB2 + group) * Cfg::H_TILE + row_in_tile * 128;
         uint32_t ra[32];
@@ -272,7 +382,7 @@ __global__ void __launch_bounds__(512, 1)
           uint32_t packed[16];
           {
             float2 o[16];
-            bias_gelu_tile16_sp<true>(ra, bias + 32 * half, o);   // 2 * gelu, see sgamma
+            bias_gelu_tile16_sp<true, FOLD>(ra, bias + 32 * half, o, fold);   // 2 * gelu, see sgamma
 #pragma unroll
             for (int j = 0; j < 16; ++j) packed[j] = Pair<bf16>::pack(o[j].x, o[j].y);
           }
@@ -307,17 +417,52 @@ __global__ void __launch_bounds__(512, 1)
     uint8_t* stg = smem + Cfg::OFF_STG + quad * 4096;
     const int sw64 = (lane >> 1) & 3;
     const int ld_piece = lane & 3, ld_row = lane >> 2;
+    // LayerNorm mode: this warp normalises its 32 rows of tile `j` in place as soon as the tile has landed
+    auto ln_tile = [&](int j) {
+      const int buf = j % Cfg::A_BUFS;
+      ptx::mbar_wait(&a_full[buf], (j / Cfg::A_BUFS) & 1);
+      const int r = quad * 32 + lane;
+      uint8_t* base = smem + Cfg::OFF_A + buf * Cfg::KB1 * Cfg::A_TILE + r * 128;
+      if (GP)
+        ln_row_in_smem<C>([&](int ch) { return base - r * 128 + ch * (Cfg::BM * 16) + r * 16; }, slnw, slnb);
+      else
+        ln_row_in_smem<C>([&](int ch) { return base + (ch >> 3) * Cfg::A_TILE + (((ch & 7) ^ (r & 7)) << 4); }, slnw, slnb);
+      ptx::fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&a_ready[buf]);
+    };
+    // FOLD mode: only the row statistics are needed (by the GELU epilogue, not by GEMM1): the tile is read, not rewritten
+    auto stats_tile = [&](int j) {
+      const int buf = j % Cfg::A_BUFS;
+      ptx::mbar_wait(&a_full[buf], (j / Cfg::A_BUFS) & 1);
+      const int r = quad * 32 + lane;
+      uint8_t* base = smem + Cfg::OFF_A + buf * Cfg::KB1 * Cfg::A_TILE;
+      sstat[(j & 1) * Cfg::BM + r] =
+          GP ? ln_row_stats_smem<C>([&](int ch) { return base + ch * (Cfg::BM * 16) + r * 16; })
+             : ln_row_stats_smem<C>([&](int ch) { return base + r * 128 + (ch >> 3) * Cfg::A_TILE + (((ch & 7) ^ (r & 7)) << 4); });
+      __syncwarp();
+      if (lane == 0) {
+        ptx::mbar_arrive(&a_ready[buf]);
+        ptx::mbar_arrive(&a_empty[buf]);
+      }
+    };
+    if (FOLD && (int)blockIdx.x < num_tiles) stats_tile(0);
+    if (!FOLD && ln && (int)blockIdx.x < num_tiles) ln_tile(0);
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int row0 = tile * Cfg::BM + quad * 32;
+      if (FOLD && tile + (int)gridDim.x < num_tiles) stats_tile(it + 1);
+      if (!FOLD && ln && tile + (int)gridDim.x < num_tiles) ln_tile(it + 1);
       auto fetch_resid = [&](int c) {
         uint8_t* dst = stg + (c & 1) * 2048;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const int rr = ld_row + 8 * q;
           const int r = row0 + rr;
-          const bf16* src = a.x + (size_t)(r < a.M ? r : 0) * C + c * 32 + ld_piece * 8;
-          const uint32_t d = ptx::smem_u32(dst + rr * 64 + ((ld_piece ^ ((rr >> 1) & 3)) << 4));
+          const bf16* src = GP ? a.x + ((size_t)(c * 4 + ld_piece) * (((size_t)a.M + 127) / 128 * 128) + (r < a.M ? r : 0)) * 8
+                               : a.x + (size_t)(r < a.M ? r : 0) * C + c * 32 + ld_piece * 8;
+          const uint32_t d = GP ? ptx::smem_u32(dst + ld_piece * 512 + rr * 16)
+                                : ptx::smem_u32(dst + rr * 64 + ((ld_piece ^ ((rr >> 1) & 3)) << 4));
           const int nbytes = r < a.M ? 16 : 0;
           asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(nbytes) : "memory");
         }
@@ -334,8 +479,10 @@ __global__ void __launch_bounds__(512, 1)
         uint32_t r[32];
         ptx::tmem_ld_32x32b_x32(lane_base + Cfg::D2_COL + c * 32, r);
         if (c + 1 < NCH) {
-          if (c >= 1) {                                          // tile (c+1)&1 was last used by chunk c-1's store
-            if (lane == 0) ptx::tma_store_wait_read<1>();
+          if (c >= 1) {   // tile (c+1)&1 is the source of chunk c-1's store, the MOST RECENT bulk group: wait for all of
+            // them (round 1 waited with <1>, i.e. not for that one -- a write-after-read race that the slower smem reads
+            // of the 16-byte-granular 3-D store of the planar layout turned into sporadic corruption)
+            if (lane == 0) ptx::tma_store_wait_read<0>();
             __syncwarp();
           }
           fetch_resid(c + 1);
@@ -352,7 +499,8 @@ __global__ void __launch_bounds__(512, 1)
         __syncwarp();
         uint4 res[4];
 #pragma unroll
-        for (int j4 = 0; j4 < 4; ++j4) res[j4] = *reinterpret_cast<const uint4*>(tbuf + lane * 64 + ((j4 ^ sw64) << 4));
+        for (int j4 = 0; j4 < 4; ++j4)
+          res[j4] = *reinterpret_cast<const uint4*>(GP ? tbuf + j4 * 512 + lane * 16 : tbuf + lane * 64 + ((j4 ^ sw64) << 4));
         __syncwarp();
         const int n = c * 32;
 #pragma unroll
@@ -372,12 +520,13 @@ __global__ void __launch_bounds__(512, 1)
           o.z = Pair<bf16>::pack(fmaf(gB.x, __uint_as_float(r[j + 4]), bB.x + f.x), fmaf(gB.y, __uint_as_float(r[j + 5]), bB.y + f.y));
           f = Pair<bf16>::unpack(res[j4].w);
           o.w = Pair<bf16>::pack(fmaf(gB.z, __uint_as_float(r[j + 6]), bB.z + f.x), fmaf(gB.w, __uint_as_float(r[j + 7]), bB.w + f.y));
-          *reinterpret_cast<uint4*>(tbuf + lane * 64 + ((j4 ^ sw64) << 4)) = o;
+          *reinterpret_cast<uint4*>(GP ? tbuf + j4 * 512 + lane * 16 : tbuf + lane * 64 + ((j4 ^ sw64) << 4)) = o;
         }
         ptx::fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
-          ptx::tma_store_2d(&tmOut, tbuf, n, row0);
+          if (GP) ptx::tma_store_3d(&tmOut, tbuf, 0, row0 >> 5, c * 4);   // box {32 rows x 16 B, 1, 4 groups}
+          else ptx::tma_store_2d(&tmOut, tbuf, n, row0);
           ptx::tma_store_commit();
         }
       }
@@ -426,12 +575,16 @@ struct Mlp96 {
   static constexpr int OFF_STG = OFF_H + 32768;            // 8 warps x 2 KB                 16 KB
   static constexpr int OFF_BAR = OFF_STG + 8 * 2048;
   static constexpr int OFF_VEC = OFF_BAR + 256;
-  static constexpr int SMEM_BYTES = OFF_VEC + (HD + 2 * C) * 4 + 1024;
+  static constexpr int SMEM_BYTES = OFF_VEC + (2 * HD + 4 * C) * 4 + 2 * BM * 8 + 1024;   // + s[4C], row stats [2][128]
   static constexpr int D2_COL = 0, D2_STRIDE = 128, D1_COL = 256, TMEM_COLS = 512;   // D2 x2 | D1 x4 (64 columns each)
   static constexpr int W_BYTES = 3 * 16384 + 3 * 8192 + 6 * 12288;
   static_assert(SMEM_BYTES <= 227 * 1024, "smem budget");
 };
 
+// GP = group-planar activations: y and x are [C/8][M][8] (16-byte channel groups as planes), the layout the tensor-core
+// depthwise conv reads and writes with full cache lines; the y tile then arrives as ONE 3-D TMA box {8, 128 rows, 12
+// groups} = the un-swizzled canonical K-major operand layout ([group][row][16 B]: K-adjacent core matrices 2 KB apart).
+template <bool GP, bool FOLD>
 __global__ void __launch_bounds__(512, 1)
     mlp_fused96_kernel(const __grid_constant__ CUtensorMap tmYm, const __grid_constant__ CUtensorMap tmYt,
                        const __grid_constant__ CUtensorMap tmW1m, const __grid_constant__ CUtensorMap tmW1t,
@@ -450,14 +603,27 @@ __global__ void __launch_bounds__(512, 1)
   uint64_t* h_empty = bars + 13;      // [2]
   uint64_t* d2_full = bars + 15;      // [2]  D2 is double-buffered: epilogue-2 of tile i overlaps GEMM2 of tile i+1
   uint64_t* d2_empty = bars + 17;     // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
+  uint64_t* a_ready = bars + 19;      // y tile normalised in place (LayerNorm mode only)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   float* sb1 = reinterpret_cast<float*>(smem + Cfg::OFF_VEC);
   float* sb2 = sb1 + Cfg::HD;
   float* sgamma = sb2 + C;
+  float* slnw = sgamma + C;
+  float* slnb = slnw + C;
+  float* ss1 = slnb + C;                                          // FOLD: s[4C]
+  float2* sstat = reinterpret_cast<float2*>(ss1 + Cfg::HD);       // FOLD: [2][128] (rstd, -mean rstd) per row
+  const bool ln = a.ln_w != nullptr;
   for (int i = threadIdx.x; i < Cfg::HD; i += blockDim.x) sb1[i] = a.b1[i];
+  if (FOLD)
+    for (int i = threadIdx.x; i < Cfg::HD; i += blockDim.x) ss1[i] = a.ln_s[i];
+  if (ln)
+    for (int i = threadIdx.x; i < C; i += blockDim.x) {
+      slnw[i] = a.ln_w[i];
+      slnb[i] = a.ln_b[i];
+    }
   for (int i = threadIdx.x; i < C; i += blockDim.x) {
     // the hidden tile holds 2 * gelu(.), so  x + gamma (0.5 acc + b2) = x + (0.5 gamma) acc + gamma b2:
     sgamma[i] = 0.5f * a.gamma[i];       // multiplies the GEMM2 accumulator
@@ -474,7 +640,8 @@ __global__ void __launch_bounds__(512, 1)
   if (warp == 1 && ptx::elect_one()) {
     ptx::mbar_init(w_full, 1);
     ptx::mbar_init(a_full, 1);
-    ptx::mbar_init(a_empty, 1);
+    ptx::mbar_init(a_empty, FOLD ? 5 : 1);                // FOLD: the 4 statistics warps read the tile too
+    ptx::mbar_init(a_ready, 4);
     for (int s = 0; s < 4; ++s) {
       ptx::mbar_init(&d1_full[s], 1);
       ptx::mbar_init(&d1_empty[s], 4);
@@ -510,12 +677,17 @@ __global__ void __launch_bounds__(512, 1)
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
         ptx::mbar_wait(a_empty, (it & 1) ^ 1);
         ptx::mbar_arrive_expect_tx(a_full, 16384 + 8192);
-        ptx::tma_load_2d(smem + Cfg::OFF_AM, &tmYm, a_full, 0, tile * Cfg::BM);
-        ptx::tma_load_2d(smem + Cfg::OFF_AT, &tmYt, a_full, 64, tile * Cfg::BM);
         const int next = tile + gridDim.x;                        // the single y buffer cannot be loaded ahead, but
-        if (next < num_tiles) {                                   // its HBM latency can: pull the next tile into L2
-          ptx::tma_prefetch_2d(&tmYm, 0, next * Cfg::BM);
-          ptx::tma_prefetch_2d(&tmYt, 64, next * Cfg::BM);
+        if (GP) {                                                 // its HBM latency can: pull the next tile into L2
+          ptx::tma_load_3d(smem + Cfg::OFF_AM, &tmYm, a_full, 0, tile * (Cfg::BM / 32), 0);
+          if (next < num_tiles) ptx::tma_prefetch_3d(&tmYm, 0, next * (Cfg::BM / 32), 0);
+        } else {
+          ptx::tma_load_2d(smem + Cfg::OFF_AM, &tmYm, a_full, 0, tile * Cfg::BM);
+          ptx::tma_load_2d(smem + Cfg::OFF_AT, &tmYt, a_full, 64, tile * Cfg::BM);
+          if (next < num_tiles) {
+            ptx::tma_prefetch_2d(&tmYm, 0, next * Cfg::BM);
+            ptx::tma_prefetch_2d(&tmYt, 64, next * Cfg::BM);
+          }
         }
       }
     }
@@ -527,6 +699,7 @@ __global__ void __launch_bounds__(512, 1)
       const uint32_t sbase = ptx::smem_u32(smem);
       const uint64_t dAm = ptx::umma_desc_sw128_kmajor(sbase + Cfg::OFF_AM);
       const uint64_t dAt = ptx::umma_desc_sw64_kmajor(sbase + Cfg::OFF_AT);
+      const uint64_t dAg = ptx::umma_desc_nosw_kmajor(sbase + Cfg::OFF_AM, 128 * 16, 128);   // GP: [group][row][16 B]
       ptx::mbar_wait(w_full, 0);
       ptx::tc_fence_after();
       // FLAT schedule over the CTA's hidden chunks g = 6 * tile_iteration + h (64 hidden columns each):
@@ -540,7 +713,7 @@ __global__ void __launch_bounds__(512, 1)
       const uint32_t total = (uint32_t)Cfg::NC * my_tiles;
       auto gemm1 = [&](uint32_t g, int h, int it) {
         if (h == 0) {
-          ptx::mbar_wait(a_full, it & 1);
+          ptx::mbar_wait((ln && !FOLD) ? a_ready : a_full, it & 1);
           ptx::tc_fence_after();
         }
         const int db1 = g & 3;
@@ -550,10 +723,17 @@ __global__ void __launch_bounds__(512, 1)
         // W1 rows [64 h, 64 h + 64): second half of a 128-row tile starts 64 rows = 8 swizzle atoms further
         const uint64_t dBm = ptx::umma_desc_sw128_kmajor(sbase + Cfg::OFF_W1M + (h >> 1) * 16384 + (h & 1) * 8192);
         const uint64_t dBt = ptx::umma_desc_sw64_kmajor(sbase + Cfg::OFF_W1T + (h >> 1) * 8192 + (h & 1) * 4096);
+        if (GP) {   // k-step ks covers channel groups 2 ks, 2 ks + 1: 2 x 2 KB further per step
 #pragma unroll
-        for (int k = 0; k < 4; ++k) ptx::umma_bf16(d1, dAm + 2 * k, dBm + 2 * k, idesc1, k != 0 ? 1u : 0u);
+          for (int k = 0; k < 4; ++k) ptx::umma_bf16(d1, dAg + k * (4096 >> 4), dBm + 2 * k, idesc1, k != 0 ? 1u : 0u);
 #pragma unroll
-        for (int k = 0; k < 2; ++k) ptx::umma_bf16(d1, dAt + 2 * k, dBt + 2 * k, idesc1, 1u);
+          for (int k = 0; k < 2; ++k) ptx::umma_bf16(d1, dAg + (4 + k) * (4096 >> 4), dBt + 2 * k, idesc1, 1u);
+        } else {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) ptx::umma_bf16(d1, dAm + 2 * k, dBm + 2 * k, idesc1, k != 0 ? 1u : 0u);
+#pragma unroll
+          for (int k = 0; k < 2; ++k) ptx::umma_bf16(d1, dAt + 2 * k, dBt + 2 * k, idesc1, 1u);
+        }
         ptx::umma_commit(&d1_full[db1]);
         if (h == Cfg::NC - 1) ptx::umma_commit(a_empty);          // y tile consumed: the producer may load the next
       };
@@ -609,8 +789,15 @@ __global__ void __launch_bounds__(512, 1)
     const int row_in_tile = quad * 32 + lane;
     const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
     const bool tr = (warp == 4 && lane == 0);
+    LnFold fold{0ull, 0ull, ptx::smem_u32(ss1) - ptx::smem_u32(sb1)};
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      if (FOLD) {                                       // this tile's row statistics (written by the epilogue-2 warps)
+        ptx::mbar_wait(a_ready, it & 1);
+        const float2 stt = sstat[(it & 1) * Cfg::BM + row_in_tile];
+        fold.rstd2 = f2_pack(stt.x, stt.x);
+        fold.nmr2 = f2_pack(stt.y, stt.y);
+      }
       for (int hc = 0; hc < Cfg::NC / 2; ++hc) {
         const int h = 2 * hc + group;
         const uint32_t gc = (uint32_t)Cfg::NC * it + h;
@@ -638,11 +825,11 @@ __global__ void __launch_bounds__(512, 1)
         ptx::tmem_ld_32x32b_x16(t0, raA);
         ptx::tmem_ld_32x32b_x16(t0 + 16, raB);
         ptx::tmem_ld_wait_dep(raA, raB);
-        gelu_stage_ta4<false, true>(nullptr, gA, raA, bias);                       // A(0)
-        gelu_stage_ta4<false, true>(nullptr, gA + 4, raA + 8, bias + 32);
+        gelu_stage_ta4<false, true, FOLD>(nullptr, gA, raA, bias, fold);                       // A(0)
+        gelu_stage_ta4<false, true, FOLD>(nullptr, gA + 4, raA + 8, bias + 32, fold);
         ptx::tmem_ld_32x32b_x16(t0 + 32, raA);
-        gelu_stage_ta4<true, true>(gA, gB, raB, bias + 64);                        // T(0) + A(1)
-        gelu_stage_ta4<true, true>(gA + 4, gB + 4, raB + 8, bias + 96);
+        gelu_stage_ta4<true, true, FOLD>(gA, gB, raB, bias + 64, fold);                        // T(0) + A(1)
+        gelu_stage_ta4<true, true, FOLD>(gA + 4, gB + 4, raB + 8, bias + 96, fold);
         ptx::tmem_ld_32x32b_x16(t0 + 48, raB);
         gelu_stage_c8_twice_bf16(gA, pk);                                          // C(0)
         ptx::mbar_wait(&h_empty[group], ((gc >> 1) & 1) ^ 1);     // GEMM2 of this group's previous chunk has read the buffer
@@ -652,12 +839,12 @@ __global__ void __launch_bounds__(512, 1)
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&d1_empty[buf]);          // all of this warp's D1 reads landed: free for GEMM1(g+4)
         if (tr) ACX_TRACE(1, 4 * hc + 2);
-        gelu_stage_ta4<true, true>(gB, gA, raA, bias + 128);                       // T(1) + A(2)
-        gelu_stage_ta4<true, true>(gB + 4, gA + 4, raA + 8, bias + 160);
+        gelu_stage_ta4<true, true, FOLD>(gB, gA, raA, bias + 128, fold);                       // T(1) + A(2)
+        gelu_stage_ta4<true, true, FOLD>(gB + 4, gA + 4, raA + 8, bias + 160, fold);
         gelu_stage_c8_twice_bf16(gB, pk);                                          // C(1)
         store_quarter(1);
-        gelu_stage_ta4<true, true>(gA, gB, raB, bias + 192);                       // T(2) + A(3)
-        gelu_stage_ta4<true, true>(gA + 4, gB + 4, raB + 8, bias + 224);
+        gelu_stage_ta4<true, true, FOLD>(gA, gB, raB, bias + 192, fold);                       // T(2) + A(3)
+        gelu_stage_ta4<true, true, FOLD>(gA + 4, gB + 4, raB + 8, bias + 224, fold);
         gelu_stage_c8_twice_bf16(gA, pk);                                          // C(2)
         store_quarter(2);
         gelu_stage_ta4<true, false>(gB, nullptr, nullptr, 0);                      // T(3)
@@ -683,17 +870,54 @@ __global__ void __launch_bounds__(512, 1)
     const bool tr = (warp == 12 && lane == 0);
     const int sw64 = (lane >> 1) & 3;
     const int ld_piece = lane & 3, ld_row = lane >> 2;
+    // LayerNorm mode: this warp normalises its 32 rows of tile `j` in place as soon as the tile has landed (columns
+    // 0..63 in the 128B-swizzled tile, 64..95 in the 64B-swizzled tail tile)
+    auto ln_tile = [&](int j) {
+      ptx::mbar_wait(a_full, j & 1);
+      const int r = quad * 32 + lane;
+      uint8_t* am = smem + Cfg::OFF_AM + r * 128;
+      uint8_t* at = smem + Cfg::OFF_AT + r * 64;
+      if (GP)
+        ln_row_in_smem<C>([&](int ch) { return smem + Cfg::OFF_AM + ch * 2048 + r * 16; }, slnw, slnb);
+      else
+        ln_row_in_smem<C>([&](int ch) { return ch < 8 ? am + ((ch ^ (r & 7)) << 4) : at + (((ch - 8) ^ ((r >> 1) & 3)) << 4); },
+                          slnw, slnb);
+      ptx::fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(a_ready);
+    };
+    // FOLD mode: only the row statistics are needed (by the GELU epilogue, not by GEMM1): the tile is read, not rewritten
+    auto stats_tile = [&](int j) {
+      ptx::mbar_wait(a_full, j & 1);
+      const int r = quad * 32 + lane;
+      uint8_t* am = smem + Cfg::OFF_AM + r * 128;
+      uint8_t* at = smem + Cfg::OFF_AT + r * 64;
+      sstat[(j & 1) * Cfg::BM + r] =
+          GP ? ln_row_stats_smem<C>([&](int ch) { return smem + Cfg::OFF_AM + ch * 2048 + r * 16; })
+             : ln_row_stats_smem<C>([&](int ch) { return ch < 8 ? am + ((ch ^ (r & 7)) << 4) : at + (((ch - 8) ^ ((r >> 1) & 3)) << 4); });
+      __syncwarp();
+      if (lane == 0) {
+        ptx::mbar_arrive(a_ready);
+        ptx::mbar_arrive(a_empty);
+      }
+    };
+    if (FOLD && (int)blockIdx.x < num_tiles) stats_tile(0);
+    if (!FOLD && ln && (int)blockIdx.x < num_tiles) ln_tile(0);
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int row0 = tile * Cfg::BM + quad * 32;
+      if (FOLD && tile + (int)gridDim.x < num_tiles) stats_tile(it + 1);
+      if (!FOLD && ln && tile + (int)gridDim.x < num_tiles) ln_tile(it + 1);
       auto fetch_resid = [&](int c) {                            // 32 rows x 64 B of chunk c -> tile (c & 1)
         uint8_t* dst = stg + (c & 1) * 2048;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const int rr = ld_row + 8 * q;
           const int r = row0 + rr;
-          const bf16* src = a.x + (size_t)(r < a.M ? r : 0) * C + c * 32 + ld_piece * 8;
-          const uint32_t d = ptx::smem_u32(dst + rr * 64 + ((ld_piece ^ ((rr >> 1) & 3)) << 4));
+          const bf16* src = GP ? a.x + ((size_t)(c * 4 + ld_piece) * (((size_t)a.M + 127) / 128 * 128) + (r < a.M ? r : 0)) * 8
+                               : a.x + (size_t)(r < a.M ? r : 0) * C + c * 32 + ld_piece * 8;
+          const uint32_t d = GP ? ptx::smem_u32(dst + ld_piece * 512 + rr * 16)
+                                : ptx::smem_u32(dst + rr * 64 + ((ld_piece ^ ((rr >> 1) & 3)) << 4));
           const int nbytes = r < a.M ? 16 : 0;
           asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(nbytes) : "memory");
         }
@@ -711,8 +935,10 @@ __global__ void __launch_bounds__(512, 1)
         uint32_t r[32];
         ptx::tmem_ld_32x32b_x32(lane_base + Cfg::D2_COL + (it & 1) * Cfg::D2_STRIDE + c * 32, r);
         if (c + 1 < 3) {
-          if (c >= 1) {                                          // tile (c+1)&1 was last used by chunk c-1's store
-            if (lane == 0) ptx::tma_store_wait_read<1>();
+          if (c >= 1) {   // tile (c+1)&1 is the source of chunk c-1's store, the MOST RECENT bulk group: wait for all of
+            // them (round 1 waited with <1>, i.e. not for that one -- a write-after-read race that the slower smem reads
+            // of the 16-byte-granular 3-D store of the planar layout turned into sporadic corruption)
+            if (lane == 0) ptx::tma_store_wait_read<0>();
             __syncwarp();
           }
           fetch_resid(c + 1);
@@ -730,7 +956,8 @@ __global__ void __launch_bounds__(512, 1)
         __syncwarp();
         uint4 res[4];
 #pragma unroll
-        for (int j4 = 0; j4 < 4; ++j4) res[j4] = *reinterpret_cast<const uint4*>(tbuf + lane * 64 + ((j4 ^ sw64) << 4));
+        for (int j4 = 0; j4 < 4; ++j4)
+          res[j4] = *reinterpret_cast<const uint4*>(GP ? tbuf + j4 * 512 + lane * 16 : tbuf + lane * 64 + ((j4 ^ sw64) << 4));
         __syncwarp();
         const int n = c * 32;
 #pragma unroll
@@ -750,12 +977,13 @@ __global__ void __launch_bounds__(512, 1)
           o.z = Pair<bf16>::pack(fmaf(gB.x, __uint_as_float(r[j + 4]), bB.x + f.x), fmaf(gB.y, __uint_as_float(r[j + 5]), bB.y + f.y));
           f = Pair<bf16>::unpack(res[j4].w);
           o.w = Pair<bf16>::pack(fmaf(gB.z, __uint_as_float(r[j + 6]), bB.z + f.x), fmaf(gB.w, __uint_as_float(r[j + 7]), bB.w + f.y));
-          *reinterpret_cast<uint4*>(tbuf + lane * 64 + ((j4 ^ sw64) << 4)) = o;
+          *reinterpret_cast<uint4*>(GP ? tbuf + j4 * 512 + lane * 16 : tbuf + lane * 64 + ((j4 ^ sw64) << 4)) = o;
         }
         ptx::fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
-          ptx::tma_store_2d(&tmOut, tbuf, n, row0);
+          if (GP) ptx::tma_store_3d(&tmOut, tbuf, 0, row0 >> 5, c * 4);   // box {32 rows x 16 B, 1, 4 groups}
+          else ptx::tma_store_2d(&tmOut, tbuf, n, row0);
           ptx::tma_store_commit();
         }
       }
@@ -773,12 +1001,19 @@ __global__ void __launch_bounds__(512, 1)
 }
 
 static int launch_mlp96_resident(const void* y, void* x, const void* w1, const float* b1, const void* w2,
-                                 const float* b2, const float* gamma, int M, cudaStream_t st) {
+                                 const float* b2, const float* gamma, int M, const float* ln_w, const float* ln_b,
+                                 const float* ln_s, bool gp, cudaStream_t st) {
   using Cfg = Mlp96;
   CUtensorMap tmYm, tmYt, tmW1m, tmW1t, tmW2, tmOut;
-  int rc = make_tmap_2d_bf16(&tmYm, y, 96, (uint64_t)M, 192, 64, 128);
-  if (rc != ACX_OK) return rc;
-  rc = make_tmap_2d_bf16(&tmYt, y, 96, (uint64_t)M, 192, 32, 128, CU_TENSOR_MAP_SWIZZLE_64B);
+  int rc;
+  if (gp) {
+    rc = make_tmap_gp_bf16(&tmYm, y, (uint64_t)M, 12, 128, 12);
+    tmYt = tmYm;
+  } else {
+    rc = make_tmap_2d_bf16(&tmYm, y, 96, (uint64_t)M, 192, 64, 128);
+    if (rc != ACX_OK) return rc;
+    rc = make_tmap_2d_bf16(&tmYt, y, 96, (uint64_t)M, 192, 32, 128, CU_TENSOR_MAP_SWIZZLE_64B);
+  }
   if (rc != ACX_OK) return rc;
   rc = make_tmap_2d_bf16(&tmW1m, w1, 96, 384, 192, 64, 128);
   if (rc != ACX_OK) return rc;
@@ -786,9 +1021,12 @@ static int launch_mlp96_resident(const void* y, void* x, const void* w1, const f
   if (rc != ACX_OK) return rc;
   rc = make_tmap_2d_bf16(&tmW2, w2, 384, 96, 768, 64, 96);
   if (rc != ACX_OK) return rc;
-  rc = make_tmap_2d_bf16(&tmOut, x, 96, (uint64_t)M, 192, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
+  rc = gp ? make_tmap_gp_bf16(&tmOut, x, (uint64_t)M, 12, 32, 4)
+          : make_tmap_2d_bf16(&tmOut, x, 96, (uint64_t)M, 192, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
   if (rc != ACX_OK) return rc;
-  ACX_SET_MAX_SMEM(mlp_fused96_kernel, Cfg::SMEM_BYTES);
+  ACX_SET_MAX_SMEM((mlp_fused96_kernel<false, false>), Cfg::SMEM_BYTES);
+  ACX_SET_MAX_SMEM((mlp_fused96_kernel<true, false>), Cfg::SMEM_BYTES);
+  ACX_SET_MAX_SMEM((mlp_fused96_kernel<true, true>), Cfg::SMEM_BYTES);
   int dev = 0, sms = 0;
   ACX_CUDA(cudaGetDevice(&dev));
   ACX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -799,31 +1037,42 @@ static int launch_mlp96_resident(const void* y, void* x, const void* w1, const f
   a.b2 = b2;
   a.gamma = gamma;
   a.M = M;
+  a.ln_w = ln_w;
+  a.ln_b = ln_b;
+  a.ln_s = ln_s;
 #ifdef ACX_ENABLE_TRACE   // debug builds only (ACX_NVCC_EXTRA="-DACX_ENABLE_TRACE", tools/trace_mlp.py): a raw device pointer
   a.trace = getenv("ACX_TRACE_PTR") ? reinterpret_cast<unsigned long long*>(strtoull(getenv("ACX_TRACE_PTR"), nullptr, 0)) : nullptr;
 #else                     // from the environment has no place in the production entry point
   a.trace = nullptr;
 #endif
-  mlp_fused96_kernel<<<tiles < sms ? tiles : sms, 512, Cfg::SMEM_BYTES, st>>>(tmYm, tmYt, tmW1m, tmW1t, tmW2, tmOut, a);
+  const int grid = tiles < sms ? tiles : sms;
+  if (gp && ln_s) mlp_fused96_kernel<true, true><<<grid, 512, Cfg::SMEM_BYTES, st>>>(tmYm, tmYt, tmW1m, tmW1t, tmW2, tmOut, a);
+  else if (gp) mlp_fused96_kernel<true, false><<<grid, 512, Cfg::SMEM_BYTES, st>>>(tmYm, tmYt, tmW1m, tmW1t, tmW2, tmOut, a);
+  else mlp_fused96_kernel<false, false><<<grid, 512, Cfg::SMEM_BYTES, st>>>(tmYm, tmYt, tmW1m, tmW1t, tmW2, tmOut, a);
   ACX_CUDA(cudaGetLastError());
   return ACX_OK;
 }
 
 template <int C>
 static int launch_mlp(const void* y, void* x, const void* w1, const float* b1, const void* w2, const float* b2,
-                      const float* gamma, int M, cudaStream_t st) {
+                      const float* gamma, int M, const float* ln_w, const float* ln_b, const float* ln_s, bool gp,
+                      cudaStream_t st) {
   using Cfg = MlpCfg<C>;
   CUtensorMap tmY, tmW1, tmW2, tmOut;
-  int rc = make_tmap_2d_bf16(&tmY, y, C, (uint64_t)M, (uint64_t)C * 2, 64, 128);
+  ACX_CHECK(!gp || C % 64 == 0, ACX_ERR_UNSUPPORTED, "mlp_fused: the streaming kernel takes group-planar tiles for C %% 64 == 0 only");
+  int rc = gp ? make_tmap_gp_bf16(&tmY, y, (uint64_t)M, C / 8, 128, C / 8)
+              : make_tmap_2d_bf16(&tmY, y, C, (uint64_t)M, (uint64_t)C * 2, 64, 128);
   if (rc != ACX_OK) return rc;
   rc = make_tmap_2d_bf16(&tmW1, w1, C, Cfg::HD, (uint64_t)C * 2, 64, Cfg::NH);
   if (rc != ACX_OK) return rc;
   rc = make_tmap_2d_bf16(&tmW2, w2, Cfg::HD, C, (uint64_t)Cfg::HD * 2, 64, C);
   if (rc != ACX_OK) return rc;
-  rc = make_tmap_2d_bf16(&tmOut, x, C, (uint64_t)M, (uint64_t)C * 2, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
+  rc = gp ? make_tmap_gp_bf16(&tmOut, x, (uint64_t)M, C / 8, 32, 4)
+          : make_tmap_2d_bf16(&tmOut, x, C, (uint64_t)M, (uint64_t)C * 2, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
   if (rc != ACX_OK) return rc;
-  auto kern = mlp_fused_kernel<C>;
-  ACX_SET_MAX_SMEM(kern, Cfg::SMEM_BYTES);
+  ACX_SET_MAX_SMEM((mlp_fused_kernel<C, false, false>), Cfg::SMEM_BYTES);
+  ACX_SET_MAX_SMEM((mlp_fused_kernel<C, true, false>), Cfg::SMEM_BYTES);
+  ACX_SET_MAX_SMEM((mlp_fused_kernel<C, true, true>), Cfg::SMEM_BYTES);
   int dev = 0, sms = 0;
   ACX_CUDA(cudaGetDevice(&dev));
   ACX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -834,8 +1083,14 @@ static int launch_mlp(const void* y, void* x, const void* w1, const float* b1, c
   a.b2 = b2;
   a.gamma = gamma;
   a.M = M;
+  a.ln_w = ln_w;
+  a.ln_b = ln_b;
+  a.ln_s = ln_s;
   a.trace = nullptr;
-  kern<<<tiles < sms ? tiles : sms, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(tmY, tmW1, tmW2, tmOut, a);
+  const int grid = tiles < sms ? tiles : sms;
+  if (gp && ln_s) mlp_fused_kernel<C, true, true><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(tmY, tmW1, tmW2, tmOut, a);
+  else if (gp) mlp_fused_kernel<C, true, false><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(tmY, tmW1, tmW2, tmOut, a);
+  else mlp_fused_kernel<C, false, false><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(tmY, tmW1, tmW2, tmOut, a);
   ACX_CUDA(cudaGetLastError());
   return ACX_OK;
 }
@@ -844,23 +1099,49 @@ static int launch_mlp(const void* y, void* x, const void* w1, const float* b1, c
 
 using namespace acx;
 
-extern "C" int acx_mlp_fused(const void* y, void* x, const void* w1, const float* b1, const void* w2, const float* b2,
-                             const float* gamma, int M, int C, void* stream) {
-  ACX_CHECK(y && x && w1 && b1 && w2 && b2 && gamma, ACX_ERR_ARG, "mlp_fused: null pointer");
-  ACX_CHECK(M > 0, ACX_ERR_ARG, "mlp_fused: M must be positive");
+static int mlp_fused_dispatch(const char* who, const void* y, void* x, const void* w1, const float* b1, const void* w2,
+                              const float* b2, const float* gamma, int M, int C, const float* ln_w, const float* ln_b,
+                              const float* ln_s, bool gp, void* stream) {
+  ACX_CHECK(!ln_s || (gp && !ln_w && !ln_b), ACX_ERR_ARG,
+            "%s: the folded LayerNorm (ln_s) is a group-planar mode and excludes ln_w / ln_b (they are folded into w1 / b1)", who);
+  ACX_CHECK(y && x && w1 && b1 && w2 && b2 && gamma, ACX_ERR_ARG, "%s: null pointer", who);
+  ACX_CHECK(M > 0, ACX_ERR_ARG, "%s: M must be positive", who);
   ACX_CHECK(((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w1) |
               reinterpret_cast<uintptr_t>(w2)) & 15) == 0,
-            ACX_ERR_ARG, "mlp_fused: y, x, w1 and w2 must be 16-byte aligned");
+            ACX_ERR_ARG, "%s: y, x, w1 and w2 must be 16-byte aligned", who);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   switch (C) {
     case 96:
       // weight-resident kernel; the streaming variant stays reachable for A/B timing (ACX_MLP96_STREAM=1)
-      if (getenv("ACX_MLP96_STREAM")) return launch_mlp<96>(y, x, w1, b1, w2, b2, gamma, M, st);
-      return launch_mlp96_resident(y, x, w1, b1, w2, b2, gamma, M, st);
-    case 192: return launch_mlp<192>(y, x, w1, b1, w2, b2, gamma, M, st);
+      if (getenv("ACX_MLP96_STREAM") && !gp) return launch_mlp<96>(y, x, w1, b1, w2, b2, gamma, M, ln_w, ln_b, nullptr, false, st);
+      return launch_mlp96_resident(y, x, w1, b1, w2, b2, gamma, M, ln_w, ln_b, ln_s, gp, st);
+    case 192: return launch_mlp<192>(y, x, w1, b1, w2, b2, gamma, M, ln_w, ln_b, ln_s, gp, st);
     default:
-      set_error("mlp_fused: C=%d not supported (the fused kernel covers stages 0-1: C = 96, 192; wider stages exceed "
-                "the 512 TMEM columns and use acx_gemm_bf16 twice)", C);
+      set_error("%s: C=%d not supported (the fused kernel covers stages 0-1: C = 96, 192; wider stages exceed "
+                "the 512 TMEM columns and use acx_gemm_bf16 twice)", who, C);
       return ACX_ERR_UNSUPPORTED;
   }
+}
+
+extern "C" int acx_mlp_fused(const void* y, void* x, const void* w1, const float* b1, const void* w2, const float* b2,
+                             const float* gamma, int M, int C, void* stream) {
+  return mlp_fused_dispatch("mlp_fused", y, x, w1, b1, w2, b2, gamma, M, C, nullptr, nullptr, nullptr, false, stream);
+}
+
+// Same, with the Block's channels-last LayerNorm (convnext.py:78) applied to the operand tile on the SM: v is the RAW
+// depthwise-conv output (acx_dwconv_tc), never normalised in HBM.
+extern "C" int acx_mlp_fused_ln(const void* v, void* x, const float* ln_w, const float* ln_b, const void* w1,
+                                const float* b1, const void* w2, const float* b2, const float* gamma, int M, int C,
+                                void* stream) {
+  ACX_CHECK(ln_w && ln_b, ACX_ERR_ARG, "mlp_fused_ln: null LayerNorm vectors");
+  return mlp_fused_dispatch("mlp_fused_ln", v, x, w1, b1, w2, b2, gamma, M, C, ln_w, ln_b, nullptr, false, stream);
+}
+
+// Group-planar variant: v and x are [C/8][M][8] bf16 (the 16-byte channel groups of all M rows as planes) -- the layout
+// acx_dwconv_tc_gp reads and writes with full cache lines.  ln_w / ln_b may be null (v already normalised).
+extern "C" int acx_mlp_fused_gp(const void* v, void* x, const float* ln_w, const float* ln_b, const float* ln_s,
+                                const void* w1, const float* b1, const void* w2, const float* b2, const float* gamma,
+                                int M, int C, void* stream) {
+  ACX_CHECK((ln_w == nullptr) == (ln_b == nullptr), ACX_ERR_ARG, "mlp_fused_gp: ln_w and ln_b must both be given or both be null");
+  return mlp_fused_dispatch("mlp_fused_gp", v, x, w1, b1, w2, b2, gamma, M, C, ln_w, ln_b, ln_s, true, stream);
 }

@@ -93,6 +93,13 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* t
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1,
+                                            int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
 __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* tm, uint64_t* bar, int c0,
                                             int c1, int c2, int c3) {
   asm volatile(
@@ -110,6 +117,18 @@ __device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* tm, int c0, i
 }
 __device__ __forceinline__ void prefetch_l2(const void* p) {
   asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* tm, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global [%0, {%1, %2, %3}];" ::"l"(reinterpret_cast<uint64_t>(tm)),
+               "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* tm, const void* smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(tm)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
 }
 
 // smem -> global tile store (bulk async group); rows/cols outside the tensor are clipped by the TMA unit.
@@ -279,6 +298,19 @@ __device__ __forceinline__ uint64_t umma_desc_sw64_kmajor(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(1) << 46;
   d |= static_cast<uint64_t>(4) << 61;               // SWIZZLE_64B
   return d;
+}
+// K-major operand WITHOUT swizzle ("interleaved" canonical layout): 8-row x 16-byte core matrices stored as 128
+// contiguous bytes; `k_stride` = bytes between core matrices adjacent along K, `mn_stride` = bytes between core matrices
+// adjacent along M / N (8 rows further).  This is what a TMA box {8 elements, rows, k-groups} of a group-planar
+// activation tensor [C/8][M][8] produces: k_stride = rows * 16, mn_stride = 128.  (Field assignment -- LBO = K
+// direction, SBO = M/N direction -- checked on hardware by tests/test_gpu_umma.py::test_mlp_fused_group_planar.)
+__device__ __forceinline__ uint64_t umma_desc_nosw_kmajor(uint32_t smem_addr, uint32_t k_stride, uint32_t mn_stride) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>((k_stride >> 4) & 0x3FFFu) << 16;      // LBO
+  d |= static_cast<uint64_t>((mn_stride >> 4) & 0x3FFFu) << 32;     // SBO
+  d |= static_cast<uint64_t>(1) << 46;                             // descriptor version
+  return d;                                                        // layout type 0: no swizzle
 }
 // Instruction descriptor, kind::f16: A = B = bf16 (K-major), D = fp32, tile M x N.
 //   [4,6) D fmt (1 = f32)  [7,10) A fmt (1 = bf16)  [10,13) B fmt (1 = bf16)

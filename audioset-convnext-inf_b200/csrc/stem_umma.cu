@@ -45,7 +45,7 @@ __device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t& hi, uin
 __global__ void __launch_bounds__(128, 4)
     stem_umma_kernel(const float* __restrict__ logmel, const float* __restrict__ w, const float* __restrict__ bias,
                      const float* __restrict__ ln_w, const float* __restrict__ ln_b, bf16* __restrict__ out, int Tn,
-                     int n_mels, int H0, int W0, long long total) {
+                     int n_mels, int H0, int W0, long long total, int gp) {
   using Cfg = StemCfg;
   constexpr int CO = Cfg::CO;
   extern __shared__ uint8_t smem_raw[];
@@ -183,6 +183,16 @@ __global__ void __launch_bounds__(128, 4)
     const int n_valid = left < 0 ? 0 : (left < 32 ? (int)left : 32);
     uint8_t* gdst = reinterpret_cast<uint8_t*>(out) + (size_t)warp_pix0 * Cfg::ROW_BYTES;
     constexpr int PIECES = Cfg::ROW_BYTES / 16;
+    if (gp) {
+      // group-planar output [12][Mp][8] (the layout the tensor-core depthwise conv of stage 0 reads): piece pc of this
+      // warp's rows is a contiguous 16 B x n_valid run of plane pc
+      const long long mp = (total + 127) / 128 * 128;
+      for (int i = lane; i < n_valid * PIECES; i += 32) {
+        const int pc = i / n_valid, r = i - pc * n_valid;
+        *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(out) + ((size_t)pc * mp + warp_pix0 + r) * 16) =
+            *reinterpret_cast<const uint4*>(stile + r * Cfg::ROW_PITCH + pc * 16);
+      }
+    } else
     for (int i = lane; i < n_valid * PIECES; i += 32) {
       const int r = i / PIECES, pc = i % PIECES;
       *reinterpret_cast<uint4*>(gdst + (size_t)r * Cfg::ROW_BYTES + pc * 16) =
@@ -199,7 +209,7 @@ __global__ void __launch_bounds__(128, 4)
 }
 
 int launch_stem_umma(const float* logmel, const float* w, const float* bias, const float* ln_w, const float* ln_b,
-                     void* out, int B, int T, int n_mels, cudaStream_t st) {
+                     void* out, int B, int T, int n_mels, int gp, cudaStream_t st) {
   using Cfg = StemCfg;
   const int H0 = (T + 4) / 4 + 1, W0 = n_mels / 4;
   const long long total = (long long)B * H0 * W0;
@@ -211,7 +221,7 @@ int launch_stem_umma(const float* logmel, const float* w, const float* bias, con
   const long long want = 4LL * sms;                              // 4 resident CTAs per SM (4 x 128 TMEM columns)
   const int grid = (int)(tiles < want ? tiles : want);
   stem_umma_kernel<<<grid, 128, Cfg::SMEM_BYTES, st>>>(logmel, w, bias, ln_w, ln_b, reinterpret_cast<bf16*>(out), T,
-                                                       n_mels, H0, W0, total);
+                                                       n_mels, H0, W0, total, gp);
   ACX_CUDA(cudaGetLastError());
   return ACX_OK;
 }

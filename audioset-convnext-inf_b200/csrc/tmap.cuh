@@ -55,4 +55,21 @@ static inline int make_tmap_2d_bf16(CUtensorMap* tm, const void* base, uint64_t 
   return make_tmap_bf16(tm, base, 2, dims, strides, box, swizzle);
 }
 
+// Group-planar activation tensor [groups][rows_pad][8] bf16 (16-byte channel groups as planes; the plane stride is the
+// row count rounded up to 128, gp_rows_pad).  A plane is contiguous, so the map views it as rows of 256 elements (32
+// tensor rows x 16 B): (256, rows_pad / 32, groups), box {256, box_rows / 32, box_groups}, no swizzle -> smem
+// [group][row][16 B], the un-swizzled canonical K-major operand layout.  (First version: inner box = one 16-byte piece --
+// the TMA unit then works piece by piece, ~14 B/clk/SM for loads and ~9 for stores, tools/ubench/tma_gather.cu, and the
+// fused MLP lost 25 us per layer to it.)  Tensor rows >= rows only exist as padding: loads return whatever is there,
+// stores land in the padding.
+static inline uint64_t gp_rows_pad(uint64_t rows) { return (rows + 127) / 128 * 128; }
+static inline int make_tmap_gp_bf16(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t groups, uint32_t box_rows,
+                                    uint32_t box_groups) {
+  const uint64_t rp = gp_rows_pad(rows);
+  cuuint64_t dims[3] = {256, rp / 32, groups};
+  cuuint64_t strides[2] = {512, rp * 16};
+  cuuint32_t box[3] = {256, box_rows / 32, box_groups};
+  return make_tmap_bf16(tm, base, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
+}
+
 }  // namespace acx

@@ -114,11 +114,25 @@ class PackedWeights:
                     w1=g(p + "pwconv1.weight").to(adt).contiguous(), b1=g(p + "pwconv1.bias").contiguous(),
                     w2=g(p + "pwconv2.weight").to(adt).contiguous(), b2=g(p + "pwconv2.bias").contiguous(),
                     gamma=g(p + "gamma").contiguous()))
+                if precision == "bf16" and s < 2:
+                    stage[-1].update(fold_layernorm_into_pwconv1(g(p + "pwconv1.weight"), g(p + "pwconv1.bias"),
+                                                                 g(p + "norm.weight"), g(p + "norm.bias")))
             self.blocks.append(stage)
 
         # ---- head ---------------------------------------------------------------------------
         self.norm_w, self.norm_b = g("norm.weight").contiguous(), g("norm.bias").contiguous()
         self.fc_w, self.fc_b = g("head_audioset.weight").contiguous(), g("head_audioset.bias").contiguous()
+
+
+def fold_layernorm_into_pwconv1(w1, b1, ln_w, ln_b):
+    """LayerNorm (CX:78) folded into pwconv1 (CX:79) for the tensor-core depthwise-conv path, whose output v is never
+    normalised in memory:   pwconv1(LN(v)) = rstd * (v . W1'^T - mean * s) + b1'   with
+        W1' = bf16(W1 * ln_w)   (the GEMM operand),   s_j = sum_c W1'[j, c]   (of the ROUNDED operand, so that the
+        identity  sum_c (v_c - mean) W1'[j, c] = G_j - mean s_j  is exact),   b1' = b1 + W1 ln_b.
+    The kernel computes (mean, rstd) per row from the same bf16 tile it multiplies."""
+    w1f = (w1.double() * ln_w.double()[None, :]).to(torch.float32).to(torch.bfloat16).contiguous()
+    return dict(w1f=w1f, s1=w1f.double().sum(1).to(torch.float32).contiguous(),
+                b1f=(b1.double() + w1.double() @ ln_b.double()).to(torch.float32).contiguous())
 
 
 def _split_f16(x):
@@ -162,7 +176,13 @@ class Engine:
         # depthwise 7x7: "tc" = banded-Toeplitz tcgen05 GEMMs (dwconv_tc.cu) + LayerNorm pass, "simt" = CUDA-core kernel
         # with the LayerNorm fused; ACX_DWCONV_TC_STAGES picks the stages that take the tensor-core route
         self.dwconv = os.environ.get("ACX_DWCONV", "tc" if precision == "bf16" else "simt")
-        self.dwconv_tc_stages = tuple(int(c) for c in os.environ.get("ACX_DWCONV_TC_STAGES", "012"))
+        self.dwconv_tc_stages = tuple(int(c) for c in os.environ.get("ACX_DWCONV_TC_STAGES", "01"))
+        # stages 0 / 1 with the fused MLP keep their activations GROUP-PLANAR ([C/8][M][8]) between the stage's entry
+        # and its downsample layer: the tensor-core conv then moves whole cache lines (dwconv_tc.cu); ACX_GP=0 keeps NHWC
+        self.gp = os.environ.get("ACX_GP", "1") == "1"
+        # where the Block's LayerNorm runs behind the tensor-core conv: "fused" = on the operand tile inside the fused
+        # MLP kernel (stages 0-1), "pass" = acx_layernorm_rows over HBM (always for stages whose MLP is two GEMMs)
+        self.ln_mode = os.environ.get("ACX_LN", "fused")
         if precision == "fp32":
             self.frontend, self.mlp, self.dwconv = "simt", "gemm", "simt"
         # LRU of workspaces keyed by (clips, samples); each owns the CUDA graphs captured over its buffers, so a
@@ -195,9 +215,12 @@ class Engine:
             ws["spec"] = torch.empty(n * T, 2 * N_BINS, device=dev, dtype=torch.float32)
         ws["logmel"] = torch.empty(n, T, N_MELS, device=dev, dtype=torch.float32)
         m0 = n * hs[0] * 56
-        ws["x"] = torch.empty(m0 * DIMS[0], device=dev, dtype=adt)
-        ws["y"] = torch.empty(m0 * DIMS[0], device=dev, dtype=adt)
+        pad = 128 * DIMS[1]        # slack for the 128-row padded planes of the group-planar layout (stages 0 / 1)
+        ws["x"] = torch.empty(m0 * DIMS[0] + pad, device=dev, dtype=adt)
+        ws["y"] = torch.empty(m0 * DIMS[0] + pad, device=dev, dtype=adt)
         ws["hid"] = torch.empty(m0 * 4 * DIMS[0], device=dev, dtype=adt)
+        if self.precision == "bf16":
+            ws["xg"] = torch.empty(m0 * DIMS[0] + pad, device=dev, dtype=adt)      # group-planar residual stream (stages 0 / 1)
         ws["pooled"] = torch.empty(n, DIMS[3], device=dev, dtype=torch.float32)
         # static outputs so that a captured CUDA graph can be replayed for any caller-owned output tensor
         ws["scene"] = torch.empty(n, DIMS[3], device=dev, dtype=torch.float32)
@@ -256,7 +279,7 @@ class Engine:
             C = int(tag[len("mlp_fused_c"):])
             s = DIMS.index(C)
             return "tensor", 2.0 * (n * hs[s] * (56 >> s)) * C * 4 * C * 2
-        if tag.startswith(("dwconv_tc_c", "ln_rows_c")):
+        if tag.startswith(("dwconv_tc_c", "ln_rows_c", "to_gp_c")):
             C = int(tag.rsplit("_c", 1)[1])
             s = DIMS.index(C)
             return "hbm", 2.0 * n * hs[s] * (56 >> s) * C * es
@@ -316,20 +339,54 @@ class Engine:
     def _trunk(self, ws, n, st):
         w = self.w
         x, y, hid = ws["x"].data_ptr(), ws["y"].data_ptr(), ws["hid"].data_ptr()
-        self._call("stem", "acx_stem", ws["logmel"].data_ptr(), w.stem_w.data_ptr(), w.stem_b.data_ptr(),
-               w.stem_ln_w.data_ptr(), w.stem_ln_b.data_ptr(), x, n, ws["T"], N_MELS, self.adt, st)
+        fused0 = self.mlp == "fused" and self.dwconv == "tc" and 0 in self.dwconv_tc_stages and self.gp
+        stem_gp = fused0 and os.environ.get("ACX_STEM", "") != "simt"     # the stem writes stage 0's planar layout itself
+        if stem_gp:
+            self._call("stem", "acx_stem_gp", ws["logmel"].data_ptr(), w.stem_w.data_ptr(), w.stem_b.data_ptr(),
+                       w.stem_ln_w.data_ptr(), w.stem_ln_b.data_ptr(), ws["xg"].data_ptr(), n, ws["T"], N_MELS, st)
+        else:
+            self._call("stem", "acx_stem", ws["logmel"].data_ptr(), w.stem_w.data_ptr(), w.stem_b.data_ptr(),
+                       w.stem_ln_w.data_ptr(), w.stem_ln_b.data_ptr(), x, n, ws["T"], N_MELS, self.adt, st)
         Wd = 56
         for s in range(4):
             C, H = DIMS[s], ws["hs"][s]
             M = n * H * Wd
+            fused_mlp = self.mlp == "fused" and C in (96, 192)
+            tc = self.dwconv == "tc" and s in self.dwconv_tc_stages
+            gp = tc and fused_mlp and self.gp and Wd in (56, 28)
+            if gp:
+                # group-planar residual stream for this stage: xg <- x; the row-major x buffer becomes the conv output
+                xg, vg = ws["xg"].data_ptr(), x
+                if not (s == 0 and stem_gp):
+                    self._call(f"to_gp_c{C}", "acx_gp_transpose", x, xg, M, C, 1, st)
             for blk in w.blocks[s]:
-                if self.dwconv == "tc" and s in self.dwconv_tc_stages:
+                if gp:
+                    self._call(f"dwconv_tc_c{C}", "acx_dwconv_tc_gp", xg, blk["dw_w"].data_ptr(), blk["dw_b"].data_ptr(), vg, n, H, Wd, C, st)
+                    # the LayerNorm runs inside the MLP kernel: folded into pwconv1 as a rank-1 epilogue correction
+                    # ("fused", default) or applied to the operand tile in shared memory (ACX_LN=smem)
+                    if self.ln_mode == "smem":
+                        self._call(f"mlp_fused_c{C}", "acx_mlp_fused_gp", vg, xg, blk["ln_w"].data_ptr(), blk["ln_b"].data_ptr(), 0,
+                                   blk["w1"].data_ptr(), blk["b1"].data_ptr(), blk["w2"].data_ptr(), blk["b2"].data_ptr(),
+                                   blk["gamma"].data_ptr(), M, C, st)
+                    else:
+                        self._call(f"mlp_fused_c{C}", "acx_mlp_fused_gp", vg, xg, 0, 0, blk["s1"].data_ptr(),
+                                   blk["w1f"].data_ptr(), blk["b1f"].data_ptr(), blk["w2"].data_ptr(), blk["b2"].data_ptr(),
+                                   blk["gamma"].data_ptr(), M, C, st)
+                    continue
+                ln_fused = False
+                if tc:
                     self._call(f"dwconv_tc_c{C}", "acx_dwconv_tc", x, blk["dw_w"].data_ptr(), blk["dw_b"].data_ptr(), y, n, H, Wd, C, st)
-                    self._call(f"ln_rows_c{C}", "acx_layernorm_rows", y, blk["ln_w"].data_ptr(), blk["ln_b"].data_ptr(), y, M, C, st)
+                    ln_fused = fused_mlp and self.ln_mode == "fused"
+                    if not ln_fused:
+                        self._call(f"ln_rows_c{C}", "acx_layernorm_rows", y, blk["ln_w"].data_ptr(), blk["ln_b"].data_ptr(), y, M, C, st)
                 else:
                     self._call(f"dwconv_ln_c{C}", "acx_dwconv_ln", x, blk["dw_w"].data_ptr(), blk["dw_b"].data_ptr(), blk["ln_w"].data_ptr(),
                                blk["ln_b"].data_ptr(), y, n, H, Wd, C, self.adt, st)
-                if self.mlp == "fused" and C in (96, 192):
+                if ln_fused:
+                    self._call(f"mlp_fused_c{C}", "acx_mlp_fused_ln", y, x, blk["ln_w"].data_ptr(), blk["ln_b"].data_ptr(),
+                               blk["w1"].data_ptr(), blk["b1"].data_ptr(), blk["w2"].data_ptr(), blk["b2"].data_ptr(),
+                               blk["gamma"].data_ptr(), M, C, st)
+                elif fused_mlp:
                     self._call(f"mlp_fused_c{C}", "acx_mlp_fused", y, x, blk["w1"].data_ptr(), blk["b1"].data_ptr(), blk["w2"].data_ptr(),
                            blk["b2"].data_ptr(), blk["gamma"].data_ptr(), M, C, st)
                 else:
@@ -338,7 +395,10 @@ class Engine:
                                blk["b2"].data_ptr(), blk["gamma"].data_ptr(), x, st)
             if s < 3:
                 d = w.ds[s]
-                self._call(f"ln_patchify_c{C}", "acx_ln_patchify", x, d["ln_w"].data_ptr(), d["ln_b"].data_ptr(), y, n, H, Wd, C, self.adt, st)
+                if gp:
+                    self._call(f"ln_patchify_c{C}", "acx_ln_patchify_gp", xg, d["ln_w"].data_ptr(), d["ln_b"].data_ptr(), y, n, H, Wd, C, st)
+                else:
+                    self._call(f"ln_patchify_c{C}", "acx_ln_patchify", x, d["ln_w"].data_ptr(), d["ln_b"].data_ptr(), y, n, H, Wd, C, self.adt, st)
                 Wd //= 2
                 Mo = n * ws["hs"][s + 1] * Wd
                 self._gemm(y, d["w"].data_ptr(), x, Mo, 2 * C, 4 * C, N.EPI_BIAS, d["b"].data_ptr(), 0, 0, st)

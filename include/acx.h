@@ -90,6 +90,9 @@ ACX_API int acx_frontend_fused(const void* hi, const void* lo, int ld_pad, const
  * w (16, 96) fp32 = stem weight transposed to (ky*4+kx, cout). */
 ACX_API int acx_stem(const float* logmel, const float* w, const float* bias, const float* ln_w, const float* ln_b,
              void* out, int B, int T, int n_mels, int act_dtype, void* stream);
+/* bf16 mode, same stem writing the group-planar layout [12][Mp][8] (Mp = B*H0*56 rounded up to 128) directly */
+ACX_API int acx_stem_gp(const float* logmel, const float* w, const float* bias, const float* ln_w, const float* ln_b,
+                void* out, int B, int T, int n_mels, void* stream);
 
 /* ---- Block part 1: depthwise 7x7 (pad 3, bias) + channels-last LayerNorm eps 1e-6 (CX:76-78) - */
 /* x (B,H,W,C) -> y (B,H,W,C); w (49, C) act_dtype (dwconv weight transposed), W % 7 == 0. */
@@ -106,10 +109,20 @@ ACX_API int acx_dwconv_tc(const void* x, const void* w, const float* bias, void*
 ACX_API int acx_layernorm_rows(const void* in, const float* ln_w, const float* ln_b, void* out, long long M, int C,
                        void* stream);
 
+/* Group-planar hand-off layout of stages 0 / 1 in bf16 mode: [C/8][Mp][8] (M = B*H*W pixels, each 16-byte group of 8
+ * channels is a plane; the plane stride Mp is M rounded up to a multiple of 128 rows -- buffers hold C * Mp elements) -- the tensor-core depthwise conv then moves whole cache lines.  acx_gp_transpose converts
+ * (M, C) row-major <-> planar (to_gp = 1 / 0); acx_dwconv_tc_gp is acx_dwconv_tc on planar x / v (W in {56, 28}). */
+ACX_API int acx_dwconv_tc_gp(const void* x, const void* w, const float* bias, void* v, int B, int H, int W, int C,
+                     void* stream);
+ACX_API int acx_gp_transpose(const void* in, void* out, long long M, int C, int to_gp, void* stream);
+
 /* ---- downsample prologue: channels_first LayerNorm + 2x2/s2 patch gather (CX:231-234) ------- */
 /* x (B,H,W,C) -> a (B*(H/2)*(W/2), 4C) with k = (dy*2+dx)*C + c  (the GEMM A operand). */
 ACX_API int acx_ln_patchify(const void* x, const float* ln_w, const float* ln_b, void* a, int B, int H, int W, int C,
                     int act_dtype, void* stream);
+/* same, x group-planar [C/8][B*H*W][8] bf16 (C = 96 / 192); `a` row-major as above */
+ACX_API int acx_ln_patchify_gp(const void* x, const float* ln_w, const float* ln_b, void* a, int B, int H, int W, int C,
+                       void* stream);
 
 /* ---- GEMMs: out[M,N] = epi(A[M,K] . W[N,K]^T)  (nn.Linear / conv-as-GEMM weight layout) ------ */
 /* bf16 operands, fp32 accumulation in TMEM (tcgen05.mma, TMA-fed).  K % 8 == 0, N % 32 == 0. */
@@ -127,6 +140,21 @@ ACX_API int acx_gemm_f32(const float* A, long long batch_stride, int rows_per_ba
  * w1 (4C,C), w2 (C,4C) bf16.  The 4C hidden tile lives in TMEM/SMEM only.  C in {96,192}. */
 ACX_API int acx_mlp_fused(const void* y, void* x, const void* w1, const float* b1, const void* w2, const float* b2,
                   const float* gamma, int M, int C, void* stream);
+/* Same with the Block's channels-last LayerNorm (CX:78, eps 1e-6) applied to the operand tile in shared memory:
+ * v (M, C) bf16 is the RAW depthwise-conv output of acx_dwconv_tc; no normalised copy ever exists in HBM. */
+ACX_API int acx_mlp_fused_ln(const void* v, void* x, const float* ln_w, const float* ln_b, const void* w1,
+                     const float* b1, const void* w2, const float* b2, const float* gamma, int M, int C,
+                     void* stream);
+/* Group-planar variant: v and x are [C/8][Mp][8] bf16 (each 16-byte group of 8 channels of all rows is a plane, plane
+ * stride Mp = M rounded up to 128), the hand-off layout of acx_dwconv_tc_gp.  Three LayerNorm modes:
+ *   ln_w = ln_b = ln_s = NULL   v is already normalised;
+ *   ln_w, ln_b given            the LayerNorm is applied to the operand tile in shared memory;
+ *   ln_s given (ln_w/ln_b NULL) FOLDED: w1 = bf16(W1 diag(ln_w)), b1 = b1 + W1 ln_b, ln_s[j] = sum_c w1[j, c]; the kernel
+ *                               computes per-row statistics only and applies the LayerNorm as a rank-1 correction
+ *                               rstd (G - mean s) + b1 in the GELU epilogue. */
+ACX_API int acx_mlp_fused_gp(const void* v, void* x, const float* ln_w, const float* ln_b, const float* ln_s,
+                     const void* w1, const float* b1, const void* w2, const float* b2, const float* gamma, int M, int C,
+                     void* stream);
 
 /* ---- tail: mean over mel, max_t + mean_t, LayerNorm(768), fc 768->527, sigmoid (CX:279-285, 321-325) */
 /* x (B,H,W,C) act_dtype -> scene (B,C) fp32 [post-LN], logits (B,n_cls), probs (B,n_cls).

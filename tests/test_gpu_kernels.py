@@ -173,8 +173,8 @@ def test_dwconv_tc_then_layernorm_rows(sd, stage, H, B):
     torch.cuda.synchronize()
     vf = v.float().cpu()
     assert torch.isfinite(vf).all(), "unwritten outputs"
-    ulp = torch.maximum(conv.abs(), torch.tensor(2.0 ** -126)) * 2.0 ** -8
-    assert ((vf - conv).abs() <= 0.51 * ulp + 1e-6).all(), (vf - conv).abs().max().item()
+    spacing = 2.0 ** (torch.floor(torch.log2(conv.abs().clamp_min(2.0 ** -100))) - 7)     # bf16 spacing at |conv|
+    assert ((vf - conv).abs() <= 0.51 * spacing + 1e-6).all(), ((vf - conv).abs() / spacing).max().item()
     y = torch.empty_like(v)
     N.call("acx_layernorm_rows", v.data_ptr(), lw.data_ptr(), lb.data_ptr(), y.data_ptr(), B * H * Wd, C, _st())
     err = (y.float().cpu() - ref).abs().max().item()
@@ -182,6 +182,47 @@ def test_dwconv_tc_then_layernorm_rows(sd, stage, H, B):
     # in place
     N.call("acx_layernorm_rows", v.data_ptr(), lw.data_ptr(), lb.data_ptr(), v.data_ptr(), B * H * Wd, C, _st())
     assert torch.equal(v, y)
+
+
+@pytest.mark.parametrize("stage,H,B", [(0, 13, 2), (0, 252, 3), (0, 130, 2), (1, 126, 2), (1, 9, 3), (1, 64, 1)])
+def test_dwconv_tc_group_planar(sd, stage, H, B):
+    """acx_dwconv_tc_gp on the group-planar hand-off layout [C/8][B*H*W][8] (stages 0 / 1): bit-identical to the NHWC
+    kernel (same MMAs, only the addressing differs), exact against F.conv2d up to the bf16 rounding of the result;
+    acx_gp_transpose round-trips and equals the torch permutation; acx_ln_patchify_gp == acx_ln_patchify."""
+    C, Wd = O.DIMS[stage], 56 >> stage
+    p = f"stages.{stage}.2."
+    g = torch.Generator().manual_seed(stage * 77 + H)
+    xq = (torch.randn(B, H, Wd, C, generator=g) * 1.5).to(torch.bfloat16)
+    wq = sd[p + "dwconv.weight"].to(torch.bfloat16)
+    conv = F.conv2d(xq.float().permute(0, 3, 1, 2), wq.float(), sd[p + "dwconv.bias"], padding=3, groups=C)
+    conv = conv.permute(0, 2, 3, 1).contiguous()
+    w = wq.reshape(C, 49).t().contiguous().to(DEV)
+    b = sd[p + "dwconv.bias"].to(DEV)
+    xd = xq.to(DEV)
+    M = B * H * Wd
+    Mp = (M + 127) // 128 * 128                                   # plane stride: rows rounded up to 128
+    xg = torch.zeros(C // 8, Mp, 8, device=DEV, dtype=torch.bfloat16)
+    N.call("acx_gp_transpose", xd.data_ptr(), xg.data_ptr(), M, C, 1, _st())
+    assert torch.equal(xg[:, :M], xd.view(M, C // 8, 8).permute(1, 0, 2)) and (xg[:, M:] == 0).all()
+    vg = torch.full_like(xg, float("nan"))
+    N.call("acx_dwconv_tc_gp", xg.data_ptr(), w.data_ptr(), b.data_ptr(), vg.data_ptr(), B, H, Wd, C, _st())
+    v = torch.empty(B, H, Wd, C, device=DEV, dtype=torch.bfloat16)
+    N.call("acx_gp_transpose", vg.data_ptr(), v.data_ptr(), M, C, 0, _st())
+    v_nhwc = torch.empty_like(v)
+    N.call("acx_dwconv_tc", xd.data_ptr(), w.data_ptr(), b.data_ptr(), v_nhwc.data_ptr(), B, H, Wd, C, _st())
+    torch.cuda.synchronize()
+    vf = v.float().cpu()
+    assert torch.isfinite(vf).all(), "unwritten outputs"
+    spacing = 2.0 ** (torch.floor(torch.log2(conv.abs().clamp_min(2.0 ** -100))) - 7)
+    assert ((vf - conv).abs() <= 0.51 * spacing + 1e-6).all(), ((vf - conv).abs() / spacing).max().item()
+    assert torch.equal(v, v_nhwc)
+    if H % 2 == 0:
+        lw, lb = sd[f"downsample_layers.{stage + 1}.0.weight"].to(DEV), sd[f"downsample_layers.{stage + 1}.0.bias"].to(DEV)
+        a0 = torch.empty(M // 4, 4 * C, device=DEV, dtype=torch.bfloat16)
+        a1 = torch.empty_like(a0)
+        N.call("acx_ln_patchify", xd.data_ptr(), lw.data_ptr(), lb.data_ptr(), a0.data_ptr(), B, H, Wd, C, N.ACX_BF16, _st())
+        N.call("acx_ln_patchify_gp", xg.data_ptr(), lw.data_ptr(), lb.data_ptr(), a1.data_ptr(), B, H, Wd, C, _st())
+        assert torch.equal(a0, a1)
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])

@@ -325,3 +325,57 @@ def test_demo_script_runs_resample_pad_and_three_outputs(tmp_path):
     assert "logits size: (1, 527)" in r.stdout
     assert "Scene embedding, shape: (1, 768)" in r.stdout
     assert "Frame-level embeddings, shape: (1, 768, 31, 7)" in r.stdout
+
+
+def test_workspace_lru_keeps_shapes_and_graphs_across_alternating_lengths(models):
+    """Engine._workspace is an LRU over (clips, samples) shapes and each workspace owns its CUDA graphs: alternating
+    lengths (variable-length extraction, ragged last batches) must neither re-allocate nor re-capture per call, a shape
+    is captured on its second use only, and replayed results equal eager ones bit for bit."""
+    m = models["bf16"]
+    eng = m._get_engine()
+    if not eng.use_graph:
+        pytest.skip("graphs disabled (ACX_GRAPH=0)")
+    eng._ws.clear()
+    La, Lb = 32000, 48000
+    wa = weights.make_waveforms(3, n_samples=La, kind="noise", seed=70).to(DEV)
+    wb = weights.make_waveforms(2, n_samples=Lb, kind="noise", seed=71).to(DEV)
+    first_a = m(wa)["clipwise_logits"].clone()                      # eager (first use of the shape)
+    first_b = m(wb)["clipwise_logits"].clone()
+    assert set(eng._ws) == {(3, La), (2, Lb)}
+    assert not eng._ws[(3, La)]["graphs"] and not eng._ws[(2, Lb)]["graphs"]
+    ids = {k: id(v) for k, v in eng._ws.items()}
+    for _ in range(3):                                              # alternate: second use captures, later uses replay
+        assert torch.equal(m(wa)["clipwise_logits"], first_a)
+        assert torch.equal(m(wb)["clipwise_logits"], first_b)
+    assert {k: id(v) for k, v in eng._ws.items()} == ids            # no re-allocation
+    assert len(eng._ws[(3, La)]["graphs"]) == 1 and len(eng._ws[(2, Lb)]["graphs"]) == 1
+    ga = next(iter(eng._ws[(3, La)]["graphs"].values()))[0]
+    m(wb), m(wa)
+    assert next(iter(eng._ws[(3, La)]["graphs"].values()))[0] is ga  # no re-capture
+    # eviction: least recently used shape goes first, together with its graphs
+    for i in range(eng.max_workspaces):
+        m(weights.make_waveforms(1, n_samples=20000 + 320 * i, kind="noise", seed=80 + i).to(DEV))
+    assert (3, La) not in eng._ws and len(eng._ws) == eng.max_workspaces
+
+
+def test_eval_loop_streams_a_generator_with_bounded_pinned_memory(models):
+    """evalloop.forward pulls batches from a generator one at a time (the loader overlaps the kernels) and stages
+    pageable batches through the pipeline's `depth` pinned buffers: nothing else is page-locked."""
+    from audioset_convnext_inf_b200 import evalloop
+    m = models["bf16"]
+    L = 32000
+    pulled = []
+
+    def gen():
+        for i in range(6):
+            pulled.append(i)
+            yield {"waveform": weights.make_waveforms(2, n_samples=L, kind="noise", seed=90 + i).numpy()}
+
+    out = evalloop.forward(m, gen())
+    assert pulled == list(range(6)) and out["clipwise_output"].shape == (12, 527)
+    ref = torch.cat([m(weights.make_waveforms(2, n_samples=L, kind="noise", seed=90 + i).to(DEV))["clipwise_output"]
+                     for i in range(6)]).cpu().numpy()
+    assert np.array_equal(out["clipwise_output"], ref)
+    pipe = acx.HostPipeline(m)
+    pipe.run([weights.make_waveforms(2, n_samples=L, kind="noise", seed=1) for _ in range(5)])   # pageable inputs
+    assert sum(s["stage"] is not None for s in pipe._slots) == pipe.depth                        # depth staging buffers

@@ -125,6 +125,135 @@ def test_mlp_fused_matches_reference_block_mlp(C, M):
     assert (x1.double() - x2.double()).abs().max().item() < 0.05      # same arithmetic up to bf16 rounding of outputs
 
 
+@pytest.mark.parametrize("C,M", [(96, 128 * 150 + 77), (96, 100), (192, 128 * 149 + 5), (192, 4000)])
+def test_mlp_fused_ln_equals_layernorm_pass_then_mlp(C, M):
+    """acx_mlp_fused_ln (LayerNorm applied to the operand tile in shared memory, CX:78-86 in one kernel) against
+    acx_layernorm_rows + acx_mlp_fused on the same raw conv output -- same arithmetic up to the summation order of the
+    LayerNorm statistics -- and against an fp64 evaluation.  Rows carry a large common offset (the shifted single-pass
+    variance must not cancel) and the tile count exceeds the 148 persistent CTAs (several tiles per CTA)."""
+    g = torch.Generator().manual_seed(7 * C + M)
+    v = (torch.randn(M, C, generator=g) * torch.rand(M, 1, generator=g) * 3 + torch.randn(M, 1, generator=g) * 20).to(torch.bfloat16)
+    x = torch.randn(M, C, generator=g).to(torch.bfloat16)
+    w1 = (torch.randn(4 * C, C, generator=g) / C ** 0.5).to(torch.bfloat16)
+    w2 = (torch.randn(C, 4 * C, generator=g) / (4 * C) ** 0.5).to(torch.bfloat16)
+    b1 = torch.randn(4 * C, generator=g) * 0.1
+    b2 = torch.randn(C, generator=g) * 0.1
+    gamma = torch.rand(C, generator=g) * 0.5 + 0.1
+    lw = torch.rand(C, generator=g) * 0.4 + 0.8
+    lb = torch.randn(C, generator=g) * 0.05
+    vd, xd, w1d, w2d, b1d, b2d, gd, lwd, lbd = (t.to(DEV) for t in (v, x, w1, w2, b1, b2, gamma, lw, lb))
+    st = torch.cuda.current_stream().cuda_stream
+    y = torch.empty_like(vd)
+    N.call("acx_layernorm_rows", vd.data_ptr(), lwd.data_ptr(), lbd.data_ptr(), y.data_ptr(), M, C, st)
+    x_pass = xd.clone()
+    N.call("acx_mlp_fused", y.data_ptr(), x_pass.data_ptr(), w1d.data_ptr(), b1d.data_ptr(), w2d.data_ptr(), b2d.data_ptr(),
+           gd.data_ptr(), M, C, st)
+    x_fused = xd.clone()
+    v_before = vd.clone()
+    N.call("acx_mlp_fused_ln", vd.data_ptr(), x_fused.data_ptr(), lwd.data_ptr(), lbd.data_ptr(), w1d.data_ptr(), b1d.data_ptr(),
+           w2d.data_ptr(), b2d.data_ptr(), gd.data_ptr(), M, C, st)
+    torch.cuda.synchronize()
+    assert torch.equal(vd, v_before)                                   # the HBM copy of v is never written
+    yn = F.layer_norm(vd.double(), (C,), lwd.double(), lbd.double(), 1e-6)
+    ref = xd.double() + gd.double() * (F.gelu(yn @ w1d.double().t() + b1d.double()) @ w2d.double().t() + b2d.double())
+    assert torch.isfinite(x_fused.float()).all()
+    d = (x_fused.double() - x_pass.double()).abs()
+    assert d.max().item() < 0.05 and (d > 0).double().mean().item() < 0.05, (d.max().item(), (d > 0).double().mean().item())
+    assert (x_fused.double() - ref).abs().max().item() < 0.05 + 0.01 * ref.abs().max().item()
+
+
+def _to_gp(t):
+    """(M, C) -> group-planar [C/8][M][8]"""
+    M, C = t.shape
+    Mp = (M + 127) // 128 * 128                      # plane stride: rows rounded up to 128
+    out = torch.zeros(C // 8, Mp, 8, device=t.device, dtype=t.dtype)
+    out[:, :M] = t.view(M, C // 8, 8).permute(1, 0, 2)
+    return out
+
+
+def _from_gp(t, M, C):
+    return t.view(C // 8, -1, 8)[:, :M].permute(1, 0, 2).reshape(M, C).contiguous()
+
+
+@pytest.mark.parametrize("ln", [False, True])
+@pytest.mark.parametrize("C,M", [(96, 128 * 150 + 77), (96, 100), (192, 128 * 149 + 5), (192, 300)])
+def test_mlp_fused_group_planar(C, M, ln):
+    """acx_mlp_fused_gp: the same fused MLP on group-planar activations ([C/8][M][8]; the operand tile arrives as one 3-D
+    TMA box in the un-swizzled canonical K-major layout, residual / output move as 16-byte group pieces) must reproduce
+    the row-major kernel bit for bit -- it is the same arithmetic in the same order; this also pins the LBO / SBO field
+    assignment of the un-swizzled smem descriptor on hardware."""
+    g = torch.Generator().manual_seed(11 * C + M)
+    v = (torch.randn(M, C, generator=g) * 2 + torch.randn(M, 1, generator=g) * 5).to(torch.bfloat16)
+    x = torch.randn(M, C, generator=g).to(torch.bfloat16)
+    w1 = (torch.randn(4 * C, C, generator=g) / C ** 0.5).to(torch.bfloat16)
+    w2 = (torch.randn(C, 4 * C, generator=g) / (4 * C) ** 0.5).to(torch.bfloat16)
+    b1 = torch.randn(4 * C, generator=g) * 0.1
+    b2 = torch.randn(C, generator=g) * 0.1
+    gamma = torch.rand(C, generator=g) * 0.5 + 0.1
+    lw = torch.rand(C, generator=g) * 0.4 + 0.8
+    lb = torch.randn(C, generator=g) * 0.05
+    vd, xd, w1d, w2d, b1d, b2d, gd, lwd, lbd = (t.to(DEV) for t in (v, x, w1, w2, b1, b2, gamma, lw, lb))
+    st = torch.cuda.current_stream().cuda_stream
+    x_rm = xd.clone()
+    if ln:
+        N.call("acx_mlp_fused_ln", vd.data_ptr(), x_rm.data_ptr(), lwd.data_ptr(), lbd.data_ptr(), w1d.data_ptr(), b1d.data_ptr(),
+               w2d.data_ptr(), b2d.data_ptr(), gd.data_ptr(), M, C, st)
+    else:
+        N.call("acx_mlp_fused", vd.data_ptr(), x_rm.data_ptr(), w1d.data_ptr(), b1d.data_ptr(), w2d.data_ptr(), b2d.data_ptr(),
+               gd.data_ptr(), M, C, st)
+    v_gp, x_gp = _to_gp(vd), _to_gp(xd)
+    N.call("acx_mlp_fused_gp", v_gp.data_ptr(), x_gp.data_ptr(), lwd.data_ptr() if ln else 0, lbd.data_ptr() if ln else 0, 0,
+           w1d.data_ptr(), b1d.data_ptr(), w2d.data_ptr(), b2d.data_ptr(), gd.data_ptr(), M, C, st)
+    torch.cuda.synchronize()
+    got = _from_gp(x_gp, M, C)
+    assert torch.isfinite(got.float()).all()
+    d = (got.float() - x_rm.float()).abs().max().item()
+    assert torch.equal(got, x_rm), d
+    assert torch.equal(v_gp[:, :M], _to_gp(vd)[:, :M])
+
+
+@pytest.mark.parametrize("C,M", [(96, 128 * 150 + 77), (96, 100), (192, 128 * 149 + 5), (192, 300)])
+def test_mlp_fused_group_planar_folded_layernorm(C, M):
+    """LayerNorm folded into pwconv1 (engine.fold_layernorm_into_pwconv1): the kernel multiplies the UN-normalised conv
+    output by W1' = bf16(W1 ln_w) and applies  rstd (G - mean s) + b1'  in the GELU epilogue.  Checked against an fp64
+    evaluation of CX:78-86 on the same bf16 inputs and against the in-shared-memory LayerNorm variant, on rows with a
+    common offset several times their spread (where the fold's cancellation is at its worst)."""
+    from audioset_convnext_inf_b200.engine import fold_layernorm_into_pwconv1
+    g = torch.Generator().manual_seed(13 * C + M)
+    v = (torch.randn(M, C, generator=g) * (torch.rand(M, 1, generator=g) * 2 + 0.2) + torch.randn(M, 1, generator=g) * 4).to(torch.bfloat16)
+    x = torch.randn(M, C, generator=g).to(torch.bfloat16)
+    w1 = torch.randn(4 * C, C, generator=g) / C ** 0.5
+    w2 = (torch.randn(C, 4 * C, generator=g) / (4 * C) ** 0.5).to(torch.bfloat16)
+    b1 = torch.randn(4 * C, generator=g) * 0.1
+    b2 = torch.randn(C, generator=g) * 0.1
+    gamma = torch.rand(C, generator=g) * 0.5 + 0.1
+    lw = torch.rand(C, generator=g) * 0.4 + 0.8
+    lb = torch.randn(C, generator=g) * 0.05
+    f = fold_layernorm_into_pwconv1(w1, b1, lw, lb)
+    vd, xd, w2d, b2d, gd, lwd, lbd, b1d = (t.to(DEV) for t in (v, x, w2, b2, gamma, lw, lb, b1))
+    w1d = w1.to(torch.bfloat16).to(DEV)
+    w1f, s1, b1f = (f[k].to(DEV) for k in ("w1f", "s1", "b1f"))
+    st = torch.cuda.current_stream().cuda_stream
+    v_gp, x_fold, x_smem = _to_gp(vd), _to_gp(xd), _to_gp(xd)
+    N.call("acx_mlp_fused_gp", v_gp.data_ptr(), x_fold.data_ptr(), 0, 0, s1.data_ptr(), w1f.data_ptr(), b1f.data_ptr(),
+           w2d.data_ptr(), b2d.data_ptr(), gd.data_ptr(), M, C, st)
+    N.call("acx_mlp_fused_gp", v_gp.data_ptr(), x_smem.data_ptr(), lwd.data_ptr(), lbd.data_ptr(), 0, w1d.data_ptr(), b1d.data_ptr(),
+           w2d.data_ptr(), b2d.data_ptr(), gd.data_ptr(), M, C, st)
+    torch.cuda.synchronize()
+    yn = F.layer_norm(vd.double(), (C,), lwd.double(), lbd.double(), 1e-6)
+    ref = xd.double() + gd.double() * (F.gelu(yn @ w1.double().to(DEV).t() + b1d.double()) @ w2d.double().t() + b2d.double())
+    got, alt = _from_gp(x_fold, M, C), _from_gp(x_smem, M, C)
+    assert torch.isfinite(got.float()).all()
+    e_fold = (got.double() - ref).abs().max().item()
+    e_smem = (alt.double() - ref).abs().max().item()
+    print(f"  folded LN max err {e_fold:.3e}, in-smem LN max err {e_smem:.3e} (ref max {ref.abs().max().item():.2f})")
+    assert e_fold < 0.05 + 0.01 * ref.abs().max().item()
+    assert e_fold < 2.5 * e_smem + 0.02
+    rc = N.load().acx_mlp_fused_gp(v_gp.data_ptr(), x_fold.data_ptr(), lwd.data_ptr(), lbd.data_ptr(), s1.data_ptr(), w1f.data_ptr(),
+                                   b1f.data_ptr(), w2d.data_ptr(), b2d.data_ptr(), gd.data_ptr(), M, C, st)
+    assert rc != 0 and "excludes" in N.last_error()
+
+
 def test_mlp_fused_rejects_wide_stages():
     t = torch.zeros(128, 384, device=DEV, dtype=torch.bfloat16)
     f = torch.zeros(1536, device=DEV)

@@ -227,3 +227,26 @@ def test_checkpoint_format_is_not_sniffed_from_leading_bytes(tmp_path):
         assert open(p, "rb").read(len(want_low)) == want_low
         m = acx.ConvNeXt.from_pretrained(p)
         assert torch.equal(m.state_dict()["stages.2.4.dwconv.weight"], sd["stages.2.4.dwconv.weight"])
+
+
+def test_layernorm_fold_into_pwconv1_is_an_identity():
+    """engine.fold_layernorm_into_pwconv1: pwconv1(LN(v)) == rstd * (v W1'^T - mean s) + b1' exactly (fp64), with the
+    bf16-rounded W1' used consistently for the GEMM operand and for s (CX:78-79)."""
+    from audioset_convnext_inf_b200.engine import fold_layernorm_into_pwconv1
+    g = torch.Generator().manual_seed(5)
+    C = 96
+    v = (torch.randn(50, C, generator=g) * 2 + torch.randn(50, 1, generator=g) * 3).to(torch.bfloat16).double()
+    w1, b1 = torch.randn(4 * C, C, generator=g) / C ** 0.5, torch.randn(4 * C, generator=g) * 0.1
+    lw, lb = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g) * 0.1
+    f = fold_layernorm_into_pwconv1(w1, b1, lw, lb)
+    assert f["w1f"].dtype == torch.bfloat16 and f["s1"].shape == (4 * C,) and f["b1f"].shape == (4 * C,)
+    mean = v.mean(1, keepdim=True)
+    rstd = 1.0 / torch.sqrt(v.var(1, unbiased=False, keepdim=True) + 1e-6)
+    folded = rstd * (v @ f["w1f"].double().t() - mean * f["s1"].double()[None]) + f["b1f"].double()[None]
+    # reference with the SAME rounded operand W1' = bf16(W1 ln_w): LN without affine, then W1', then the folded bias
+    direct = ((v - mean) * rstd) @ f["w1f"].double().t() + f["b1f"].double()[None]
+    assert (folded - direct).abs().max().item() < 1e-5
+    # and against the unfolded layer: differs only by the bf16 rounding of W1 ln_w
+    ln = torch.nn.functional.layer_norm(v, (C,), lw.double(), lb.double(), 1e-6)
+    exact = ln @ w1.double().t() + b1.double()[None]
+    assert (folded - exact).abs().max().item() < 0.05
