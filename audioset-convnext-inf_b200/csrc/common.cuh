@@ -145,8 +145,8 @@ __device__ __forceinline__ void gelu_op_tanh(GeluPair& g) {
 // the biases in shared memory).  One extra packed FMA per column pair instead of a LayerNorm pass over the tensor.
 struct LnFold {
   unsigned long long rstd2, nmr2;
-  uint32_t s_off;
-};
+  uint32_t sb1_base, sbs_base;   // smem addresses of b1[] and of the interleaved {b1[2q], b1[2q+1], s[2q], s[2q+1]} array:
+};                               // ONE 16-byte load brings a column pair's biases and s (a second 8-byte load cost 9 %)
 template <bool kT, bool kA, bool kFold = false>
 __device__ __forceinline__ void gelu_stage_ta4(GeluPair* t, GeluPair* a, const uint32_t* acc, uint32_t sbias_addr,
                                                const LnFold fold = LnFold{}) {
@@ -160,16 +160,18 @@ __device__ __forceinline__ void gelu_stage_ta4(GeluPair* t, GeluPair* a, const u
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       float2 b;
-      asm("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(b.x), "=f"(b.y) : "r"(sbias_addr + 8 * i));
       if (kFold) {
         float2 sj;
-        asm("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(sj.x), "=f"(sj.y) : "r"(sbias_addr + fold.s_off + 8 * i));
+        asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+            : "=f"(b.x), "=f"(b.y), "=f"(sj.x), "=f"(sj.y)
+            : "r"(fold.sbs_base + 2 * (sbias_addr - fold.sb1_base) + 16 * i));
         unsigned long long tt;
         asm volatile("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(tt) : "l"(fold.nmr2), "l"(f2_pack(sj.x, sj.y)), "l"(f2_pack(b.x, b.y)));
         asm volatile("fma.rn.f32x2 %0, %1, %2, %3;"
                      : "=l"(a[i].x)
                      : "l"(fold.rstd2), "l"(f2_pack(__uint_as_float(acc[2 * i]), __uint_as_float(acc[2 * i + 1]))), "l"(tt));
       } else {
+        asm("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(b.x), "=f"(b.y) : "r"(sbias_addr + 8 * i));
         asm volatile("add.rn.f32x2 %0, %1, %2;"
                      : "=l"(a[i].x)
                      : "l"(f2_pack(__uint_as_float(acc[2 * i]), __uint_as_float(acc[2 * i + 1]))), "l"(f2_pack(b.x, b.y)));

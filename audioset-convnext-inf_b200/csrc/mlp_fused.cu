@@ -134,7 +134,7 @@ struct MlpCfg {
   static constexpr int STG_PER_WARP = STG_TILE;       // one tile: residual transpose in, output staging out
   static constexpr int OFF_BAR = OFF_STG + 8 * STG_PER_WARP;
   static constexpr int OFF_VEC = OFF_BAR + 512;       // b1[4C], b2[C], gamma[C], ln_w[C], ln_b[C] staged once per CTA
-  static constexpr int SMEM_BYTES = OFF_VEC + (2 * HD + 4 * C) * 4 + 2 * BM * 8 + 1024;   // + s[4C], row stats [2][128]
+  static constexpr int SMEM_BYTES = OFF_VEC + (3 * HD + 4 * C) * 4 + 2 * BM * 8 + 1024;   // + {b1, s} interleaved [2 x 4C], row stats [2][128]
   static constexpr int D2_COL = 0, D1_COL = 256, TMEM_COLS = 512;
   static constexpr int OUT_CHUNKS = C / 32;           // 32-column output chunks: 3 / 6
   static constexpr int OUT_G0 = (OUT_CHUNKS + 1) / 2;
@@ -172,12 +172,15 @@ __global__ void __launch_bounds__(512, 1)
   float* sgamma = sb2 + C;
   float* slnw = sgamma + C;
   float* slnb = slnw + C;
-  float* ss1 = slnb + C;                                          // FOLD: s[4C]
-  float2* sstat = reinterpret_cast<float2*>(ss1 + Cfg::HD);       // FOLD: [2][128] (rstd, -mean rstd) per row
+  float* ss1 = slnb + C;                                          // FOLD: {b1[2q], b1[2q+1], s[2q], s[2q+1]} per column pair
+  float2* sstat = reinterpret_cast<float2*>(ss1 + 2 * Cfg::HD);   // FOLD: [2][128] (rstd, -mean rstd) per row
   const bool ln = a.ln_w != nullptr;
   for (int i = threadIdx.x; i < Cfg::HD; i += blockDim.x) sb1[i] = a.b1[i];
   if (FOLD)
-    for (int i = threadIdx.x; i < Cfg::HD; i += blockDim.x) ss1[i] = a.ln_s[i];
+    for (int i = threadIdx.x; i < Cfg::HD; i += blockDim.x) {
+      ss1[4 * (i >> 1) + (i & 1)] = a.b1[i];
+      ss1[4 * (i >> 1) + 2 + (i & 1)] = a.ln_s[i];
+    }
   if (ln)
     for (int i = threadIdx.x; i < C; i += blockDim.x) {
       slnw[i] = a.ln_w[i];
@@ -355,7 +358,7 @@ __global__ void __launch_bounds__(512, 1)
     const int row_in_tile = quad * 32 + lane;
     const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
     uint32_t gc = 0;
-    LnFold fold{0ull, 0ull, ptx::smem_u32(ss1) - ptx::smem_u32(sb1)};
+    LnFold fold{0ull, 0ull, ptx::smem_u32(sb1), ptx::smem_u32(ss1)};
     int it1 = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it1) {
       for (int h = 0; h < Cfg::NC; ++h, ++gc) {
@@ -575,7 +578,7 @@ struct Mlp96 {
   static constexpr int OFF_STG = OFF_H + 32768;            // 8 warps x 2 KB                 16 KB
   static constexpr int OFF_BAR = OFF_STG + 8 * 2048;
   static constexpr int OFF_VEC = OFF_BAR + 256;
-  static constexpr int SMEM_BYTES = OFF_VEC + (2 * HD + 4 * C) * 4 + 2 * BM * 8 + 1024;   // + s[4C], row stats [2][128]
+  static constexpr int SMEM_BYTES = OFF_VEC + (3 * HD + 4 * C) * 4 + 2 * BM * 8 + 1024;   // + {b1, s} interleaved [2 x 4C], row stats [2][128]
   static constexpr int D2_COL = 0, D2_STRIDE = 128, D1_COL = 256, TMEM_COLS = 512;   // D2 x2 | D1 x4 (64 columns each)
   static constexpr int W_BYTES = 3 * 16384 + 3 * 8192 + 6 * 12288;
   static_assert(SMEM_BYTES <= 227 * 1024, "smem budget");
@@ -613,12 +616,15 @@ __global__ void __launch_bounds__(512, 1)
   float* sgamma = sb2 + C;
   float* slnw = sgamma + C;
   float* slnb = slnw + C;
-  float* ss1 = slnb + C;                                          // FOLD: s[4C]
-  float2* sstat = reinterpret_cast<float2*>(ss1 + Cfg::HD);       // FOLD: [2][128] (rstd, -mean rstd) per row
+  float* ss1 = slnb + C;                                          // FOLD: {b1[2q], b1[2q+1], s[2q], s[2q+1]} per column pair
+  float2* sstat = reinterpret_cast<float2*>(ss1 + 2 * Cfg::HD);   // FOLD: [2][128] (rstd, -mean rstd) per row
   const bool ln = a.ln_w != nullptr;
   for (int i = threadIdx.x; i < Cfg::HD; i += blockDim.x) sb1[i] = a.b1[i];
   if (FOLD)
-    for (int i = threadIdx.x; i < Cfg::HD; i += blockDim.x) ss1[i] = a.ln_s[i];
+    for (int i = threadIdx.x; i < Cfg::HD; i += blockDim.x) {
+      ss1[4 * (i >> 1) + (i & 1)] = a.b1[i];
+      ss1[4 * (i >> 1) + 2 + (i & 1)] = a.ln_s[i];
+    }
   if (ln)
     for (int i = threadIdx.x; i < C; i += blockDim.x) {
       slnw[i] = a.ln_w[i];
@@ -789,7 +795,7 @@ __global__ void __launch_bounds__(512, 1)
     const int row_in_tile = quad * 32 + lane;
     const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
     const bool tr = (warp == 4 && lane == 0);
-    LnFold fold{0ull, 0ull, ptx::smem_u32(ss1) - ptx::smem_u32(sb1)};
+    LnFold fold{0ull, 0ull, ptx::smem_u32(sb1), ptx::smem_u32(ss1)};
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       if (FOLD) {                                       // this tile's row statistics (written by the epilogue-2 warps)

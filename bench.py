@@ -27,6 +27,17 @@ BATCH = 64
 N_ROTATE = 3            # 3 x 82 MB of input + ~0.5 GB of activations per chunk >> 126 MB L2
 
 
+ROOFLINE_NOTES = {
+    "mlp_fused": "fused pwconv1 -> GELU -> pwconv2 -> layer-scale -> residual; in the group-planar stages the kernel also "
+                 "computes the per-row LayerNorm statistics and applies the LayerNorm as a rank-1 epilogue correction, work "
+                 "that is not in the 16 M C^2 FLOP numerator; bound by GELU-epilogue instruction issue, not by the MMAs",
+    "dwconv_ln": "49 fp32 FMA per element on the CUDA cores: its practical roof is the FP32 pipe (~37% of the HBM figure "
+                 "at 100% FMA issue), see DESIGN.md",
+    "dwconv_tc": "banded-Toeplitz tcgen05 GEMMs (M64 N32 K16); the MMAs stream their operands out of shared memory at "
+                 "128 B/clk, which bounds the kernel at ~0.06 ms per stage-0 layer; numerator = 2 M C 2 B of HBM traffic",
+}
+
+
 def _peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(p):
@@ -448,8 +459,7 @@ def main():
                          "timed_in": "the same K steps repeated right after the timed region with individual launches "
                                      "(CUDA events cannot bracket a node of a replayed graph)",
                          "share_of_step": round(share, 4),
-                         "note": "dwconv_ln does 49 fp32 FMA per element on the CUDA cores: its practical roof is the "
-                                 "FP32 pipe (~37% of the HBM figure at 100% FMA issue), see DESIGN.md"},
+                         "note": ROOFLINE_NOTES.get(top.rsplit("_c", 1)[0], "")},
             "roofline_all": all_kernels,
         }
         res.update(extras)
