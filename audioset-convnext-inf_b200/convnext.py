@@ -187,6 +187,13 @@ class ConvNeXt(nn.Module):
             raise ValueError(f"expected a (batch, samples) waveform, got shape {tuple(x.shape)}")
         eng = self._get_engine()
         x = x.detach().to(device=eng.device, dtype=torch.float32).contiguous()
+        if os.environ.get("ACX_CHECK_AMPLITUDE") == "1" and eng.precision == "bf16" and x.numel():
+            # debugging aid (one reduction + sync per call): the bf16-mode front end carries samples as 2^8-scaled fp16
+            # pairs, so |x| must stay below 255 (input contract); the fp32-accurate mode has no such bound
+            amax = float(x.abs().amax())
+            if not amax < 255.0:
+                raise ValueError(f"waveform amplitude {amax:g} exceeds the bf16-mode front end's range (|x| < 255): "
+                                 "normalise to [-1, 1] like torchaudio.load / int16 / 32767, or use set_precision('fp32')")
         return eng, x
 
     # ---- the three inference entry points --------------------------------------------------------

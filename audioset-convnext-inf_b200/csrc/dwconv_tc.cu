@@ -336,7 +336,8 @@ __global__ void __launch_bounds__(THREADS, 2)
 //       warps 1-7   loaders: fragment loads (full 128-byte lines of the planar tensor) -> stmatrix.trans -> A[buf];
 //                   ALL rows of an item are requested in one round (10 rows = 40 loads in flight per lane): with four
 //                   warps and three dependent rounds per item the loaders were latency-bound (7.4 k cycles per item
-//                   against 2.75 k of MMA time)
+//                   against 2.75 k of MMA time); an L2 prefetch of the next item's rows changed nothing (110.8 vs 110.2 us):
+//                   the loaders are bound by their own instruction stream (40 loads + 10 stmatrix per lane and item)
 //       warp  0     112 back-to-back tcgen05.mma (M64 N32 K16) per item -> D[buf]
 //       warps 8-15  write-out: D[buf] -> + bias -> bf16 -> smem staging -> 448-byte contiguous runs of the planar output
 // =====================================================================================================================

@@ -379,3 +379,17 @@ def test_eval_loop_streams_a_generator_with_bounded_pinned_memory(models):
     pipe = acx.HostPipeline(m)
     pipe.run([weights.make_waveforms(2, n_samples=L, kind="noise", seed=1) for _ in range(5)])   # pageable inputs
     assert sum(s["stage"] is not None for s in pipe._slots) == pipe.depth                        # depth staging buffers
+
+
+def test_amplitude_contract_check_is_opt_in(models, monkeypatch):
+    """INTEGRATION.md input contract: bf16 mode carries samples as 2^8-scaled fp16 pairs (|x| < 255).  ACX_CHECK_AMPLITUDE=1
+    turns a violation into an explicit error; the fp32-accurate mode accepts any float amplitude like the reference."""
+    m = models["bf16"]
+    w = weights.make_waveforms(1, n_samples=32000, kind="noise", seed=5).to(DEV)
+    monkeypatch.setenv("ACX_CHECK_AMPLITUDE", "1")
+    assert torch.isfinite(m(w)["clipwise_logits"]).all()
+    with pytest.raises(ValueError, match="amplitude"):
+        m(w * 32767.0)
+    ref = O.forward((w * 300.0).cpu(), weights.make_state_dict("parity", 8))["clipwise_logits"]
+    got = models["fp32"](w * 300.0)["clipwise_logits"].cpu()
+    assert (got - ref).abs().max() < 5e-4
