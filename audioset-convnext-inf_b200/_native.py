@@ -31,9 +31,13 @@ SIGNATURES = {
     "acx_layernorm_rows": [_vp, _vp, _vp, _vp, _ll, _i, _vp],
     "acx_dwconv_tc_gp": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "acx_gp_transpose": [_vp, _vp, _ll, _i, _i, _vp],
+    "acx_gp_row_stats": [_vp, _vp, _ll, _i, _vp],
     "acx_ln_patchify_gp": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "acx_ln_patchify": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     "acx_gemm_bf16": [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp],
+    "acx_gemm_bf16_gp_out": [_vp, _vp, _vp, _i, _i, _i, _vp, _vp],
+    "acx_gemm_bf16_pw1_gp": [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp],
+    "acx_gemm_bf16_pw2_gp": [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp],
     "acx_gemm_f32": [_vp, _ll, _i, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp],
     "acx_mlp_fused": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp],
     "acx_mlp_fused_ln": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp],

@@ -362,6 +362,8 @@ __global__ void __launch_bounds__(THREADS, 1)
                       bf16* __restrict__ v, int n_clips, int H, int C, long long* __restrict__ trace) {
   constexpr int NHALF = W > 32 ? 2 : 1;
   constexpr int HW = NHALF == 2 ? 28 : W;
+  constexpr int KS = W <= 16 ? 1 : 2;           // K steps per (channel, dy): a 14-wide row fits ONE 16-column K window
+  constexpr int NMI = W <= 16 ? 2 : 4;          // 8-pixel blocks per row that can hold image columns
 #ifdef ACX_ENABLE_TRACE
   long long tr_wait = 0, tr_wait2 = 0, tr_work = 0, tr_t = 0, tr_n = 0;
 #define V3_T0() do { if (trace) tr_t = clock64(); } while (0)
@@ -442,7 +444,7 @@ __global__ void __launch_bounds__(THREADS, 1)
 #pragma unroll
           for (int dy = 0; dy < 7; ++dy)
 #pragma unroll
-            for (int ks = 0; ks < 2; ++ks)
+            for (int ks = 0; ks < KS; ++ks)
               ptx::umma_bf16(d, da + dy * 4 + 2 * ks, db + dy * (BAND_TILE / 16) + 2 * ks, idesc, (dy | ks) ? 1u : 0u);
         }
         ptx::umma_commit(&a_empty[buf]);
@@ -486,7 +488,7 @@ __global__ void __launch_bounds__(THREADS, 1)
 #pragma unroll
           for (int mi = 0; mi < 4; ++mi) {
             const int col = kw0 + mi * 8 + px;
-            q[u][mi] = (row_ok && col < W) ? ldg_nc_u32(xin + ((size_t)h * W + mi * 8 + px) * 8) : 0u;
+            q[u][mi] = (mi < NMI && row_ok && col < W) ? ldg_nc_u32(xin + ((size_t)h * W + mi * 8 + px) * 8) : 0u;
           }
         }
 #pragma unroll
@@ -744,8 +746,9 @@ extern "C" int acx_dwconv_tc_gp(const void* x, const void* w, const float* bias,
   switch (W) {
     case 56: return use_v1 ? dwtc::launch<56, true>(x, w, bias, v, B, H, C, st) : dwtc::v3::launch<56>(x, w, bias, v, B, H, C, st);
     case 28: return use_v1 ? dwtc::launch<28, true>(x, w, bias, v, B, H, C, st) : dwtc::v3::launch<28>(x, w, bias, v, B, H, C, st);
+    case 14: return dwtc::v3::launch<14>(x, w, bias, v, B, H, C, st);
     default:
-      set_error("dwconv_tc_gp: W=%d not supported (stages 0 / 1: 56 / 28)", W);
+      set_error("dwconv_tc_gp: W=%d not supported (stages 0 - 2: 56 / 28 / 14)", W);
       return ACX_ERR_UNSUPPORTED;
   }
 }
@@ -786,6 +789,49 @@ __global__ void __launch_bounds__(256) gp_transpose_kernel(const uint4* __restri
 }
 }  // namespace dwtc
 }  // namespace acx
+
+// Per-row LayerNorm statistics of a group-planar tensor [C/8][Mp][8] bf16: stats[row] = (rstd, -mean * rstd), eps 1e-6.
+// For the stages whose MLP is the N-tiled generic GEMM: every N tile's GELU epilogue needs the row's statistics and
+// none of them owns the row, so they are computed once here (one pass over v: thread = row, loads coalesced per plane).
+namespace acx {
+namespace dwtc {
+__global__ void __launch_bounds__(256) gp_row_stats_kernel(const uint4* __restrict__ v, float2* __restrict__ stats,
+                                                           long long M, int G) {
+  const long long row = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (row >= M) return;
+  const long long Mp = (M + 127) / 128 * 128;
+  const float inv_c = 1.0f / (8.0f * G);
+  const uint4 first = __ldg(v + row);
+  const float shift = __uint_as_float(first.x << 16);
+  const float2 sh2 = make_float2(-shift, -shift);
+  float2 s = make_float2(0.f, 0.f), q = make_float2(0.f, 0.f);
+#pragma unroll 4
+  for (int gq = 0; gq < G; ++gq) {
+    const uint4 u = __ldg(v + (long long)gq * Mp + row);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 d = __fadd2_rn(Pair<bf16>::unpack(w[k]), sh2);
+      s = __fadd2_rn(s, d);
+      q = __ffma2_rn(d, d, q);
+    }
+  }
+  const float md = (s.x + s.y) * inv_c;
+  const float var = fmaxf((q.x + q.y) * inv_c - md * md, 0.f);
+  const float rstd = rsqrtf(var + 1e-6f);
+  stats[row] = make_float2(rstd, -(md + shift) * rstd);
+}
+}  // namespace dwtc
+}  // namespace acx
+
+extern "C" int acx_gp_row_stats(const void* v, float* stats, long long M, int C, void* stream) {
+  ACX_CHECK(v && stats, ACX_ERR_ARG, "gp_row_stats: null pointer");
+  ACX_CHECK(M > 0 && C > 0 && C % 8 == 0, ACX_ERR_ARG, "gp_row_stats: bad shape M=%lld C=%d", M, C);
+  dwtc::gp_row_stats_kernel<<<(unsigned)((M + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const uint4*>(v), reinterpret_cast<float2*>(stats), M, C / 8);
+  ACX_CUDA(cudaGetLastError());
+  return ACX_OK;
+}
 
 extern "C" int acx_gp_transpose(const void* in, void* out, long long M, int C, int to_gp, void* stream) {
   ACX_CHECK(in && out && in != out, ACX_ERR_ARG, "gp_transpose: null or aliased pointers");

@@ -24,7 +24,12 @@ struct GemmArgs {
   const float* gamma;
   const bf16* resid;
   int M, N, K;
+  int out_gp;   // 1: `out` (and `resid`) are group-planar [N/8][Mp][8] (the hand-off layout of the tensor-core depthwise conv)
+  int a_gp;     // 1: A is group-planar [K/8][Mp][8]: operand tiles arrive as 3-D boxes in the un-swizzled K-major layout
+  const float2* stats;   // EPI_BIAS_GELU_FOLD: per-row (rstd, -mean * rstd) of A (acx_gp_row_stats)
+  const float* ln_s;     // EPI_BIAS_GELU_FOLD: s[j] = sum_k W[j, k] of the LayerNorm-folded weights
 };
+constexpr int ACX_EPI_BIAS_GELU_FOLD = 3;   // internal: GELU epilogue with the LayerNorm applied as a rank-1 correction
 
 // CG = 1: one CTA per 128 x BN tile.  CG = 2: a CTA PAIR (cluster of 2, tcgen05 cta_group::2) per 256 x BN tile -- each
 // CTA stages its own 128 A rows and HALF of the B rows, so operand traffic from L2 per FLOP drops by a third and the
@@ -82,9 +87,17 @@ __global__ void __launch_bounds__(GemmCfg<BN, NEPI, CG>::THREADS, 1)
   // ncu showed as the epilogue's dominant stall (long_scoreboard)
   float* sbias = reinterpret_cast<float*>(smem + Cfg::OFF_VEC);
   float* sgamma = sbias + g.N;
-  for (int i = threadIdx.x; i < g.N; i += blockDim.x) {
-    sbias[i] = g.bias[i];
-    if (EPI == ACX_EPI_BIAS_SCALE_RESID) sgamma[i] = g.gamma[i];
+  if (EPI == ACX_EPI_BIAS_GELU_FOLD) {
+    // interleaved {b[2q], b[2q+1], s[2q], s[2q+1]}: one 16-byte load per column pair in the folded epilogue
+    for (int i = threadIdx.x; i < g.N; i += blockDim.x) {
+      sbias[4 * (i >> 1) + (i & 1)] = g.bias[i];
+      sbias[4 * (i >> 1) + 2 + (i & 1)] = g.ln_s[i];
+    }
+  } else {
+    for (int i = threadIdx.x; i < g.N; i += blockDim.x) {
+      sbias[i] = g.bias[i];
+      if (EPI == ACX_EPI_BIAS_SCALE_RESID) sgamma[i] = g.gamma[i];
+    }
   }
 
   if (warp == 0 && ptx::elect_one()) {
@@ -138,11 +151,13 @@ __global__ void __launch_bounds__(GemmCfg<BN, NEPI, CG>::THREADS, 1)
           if (CG == 2) {
             // both CTAs' bytes complete on the LEADER's full barrier; only the leader arms it
             if (cta_rank == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
-            ptx::tma_load_2d_cg2(sa, &tmA, &full_bar[stage], kb * Cfg::BK, m0);
+            if (g.a_gp) ptx::tma_load_3d_cg2(sa, &tmA, &full_bar[stage], 0, m0 >> 5, kb * (Cfg::BK / 8));
+            else ptx::tma_load_2d_cg2(sa, &tmA, &full_bar[stage], kb * Cfg::BK, m0);
             ptx::tma_load_2d_cg2(sb, &tmB, &full_bar[stage], kb * Cfg::BK, n0);
           } else {
             ptx::mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-            ptx::tma_load_2d(sa, &tmA, &full_bar[stage], kb * Cfg::BK, m0);
+            if (g.a_gp) ptx::tma_load_3d(sa, &tmA, &full_bar[stage], 0, m0 >> 5, kb * (Cfg::BK / 8));
+            else ptx::tma_load_2d(sa, &tmA, &full_bar[stage], kb * Cfg::BK, m0);
             ptx::tma_load_2d(sb, &tmB, &full_bar[stage], kb * Cfg::BK, n0);
           }
           if (++stage == Cfg::STAGES) {
@@ -169,14 +184,16 @@ __global__ void __launch_bounds__(GemmCfg<BN, NEPI, CG>::THREADS, 1)
           ptx::mbar_wait(&full_bar[stage], phase);
           ptx::tc_fence_after();
           const uint32_t sa = ptx::smem_u32(smem + stage * Cfg::STAGE_BYTES);
-          const uint64_t da = ptx::umma_desc_sw128_kmajor(sa);
+          // planar A: [8 groups][128 rows][16 B] un-swizzled, a K step = two groups = 4 KB further
+          const uint64_t da = g.a_gp ? ptx::umma_desc_nosw_kmajor(sa, Cfg::BM * 16, 128) : ptx::umma_desc_sw128_kmajor(sa);
+          const uint32_t ka = g.a_gp ? (2 * Cfg::BM * 16) >> 4 : 2;
           const uint64_t db = ptx::umma_desc_sw128_kmajor(sa + Cfg::A_BYTES);
 #pragma unroll
           for (int k = 0; k < Cfg::BK / 16; ++k) {
             if (kb * Cfg::BK + k * 16 < g.K) {
               // advance 16 bf16 = 32 B along K inside the 128B swizzle row: +2 in the (addr >> 4) field
-              if (CG == 2) ptx::umma_bf16_cg2(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-              else ptx::umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+              if (CG == 2) ptx::umma_bf16_cg2(d_tmem, da + ka * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+              else ptx::umma_bf16(d_tmem, da + ka * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
             }
           }
           // smem slot reusable (in both CTAs when paired) once these MMAs retire
@@ -222,10 +239,19 @@ __global__ void __launch_bounds__(GemmCfg<BN, NEPI, CG>::THREADS, 1)
         for (int q = 0; q < 4; ++q) {
           const int r = row0 + ld_row + 8 * q;
           rq[q] = make_uint4(0u, 0u, 0u, 0u);
-          if (r < g.M) rq[q] = *reinterpret_cast<const uint4*>(g.resid + (size_t)r * g.N + n + ld_piece * 8);
+          if (r < g.M)
+            rq[q] = g.out_gp ? *reinterpret_cast<const uint4*>(g.resid + ((size_t)((n >> 3) + ld_piece) * (((size_t)g.M + 127) / 128 * 128) + r) * 8)
+                             : *reinterpret_cast<const uint4*>(g.resid + (size_t)r * g.N + n + ld_piece * 8);
         }
       };
       fetch_resid(0);   // overlaps the wait for the accumulator
+      LnFold fold{0ull, 0ull, ptx::smem_u32(sbias), ptx::smem_u32(sbias)};
+      if (EPI == ACX_EPI_BIAS_GELU_FOLD) {
+        const int r = row0 + lane;
+        const float2 stt = r < g.M ? __ldg(g.stats + r) : make_float2(0.f, 0.f);
+        fold.rstd2 = f2_pack(stt.x, stt.x);
+        fold.nmr2 = f2_pack(stt.y, stt.y);
+      }
       ptx::mbar_wait(&tfull_bar[acc], acc_phase);
       ptx::tc_fence_after();
       const uint32_t t_base = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * Cfg::ACC_STRIDE +
@@ -250,7 +276,15 @@ __global__ void __launch_bounds__(GemmCfg<BN, NEPI, CG>::THREADS, 1)
           }
           const int n = n0 + (ch_begin + ci) * Cfg::CHUNK;
           float v[32];
-          if (EPI == ACX_EPI_BIAS_GELU) {
+          if (EPI == ACX_EPI_BIAS_GELU_FOLD) {
+            float2 o[16];
+            bias_gelu_tile16_sp<false, true>(r, sbias + n, o, fold);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              v[2 * j] = o[j].x;
+              v[2 * j + 1] = o[j].y;
+            }
+          } else if (EPI == ACX_EPI_BIAS_GELU) {
             float2 o[16];
             bias_gelu_tile16_sp<false>(r, sbias + n, o);
 #pragma unroll
@@ -303,12 +337,14 @@ __global__ void __launch_bounds__(GemmCfg<BN, NEPI, CG>::THREADS, 1)
             q.y = Pair<bf16>::pack(v[j + 2], v[j + 3]);
             q.z = Pair<bf16>::pack(v[j + 4], v[j + 5]);
             q.w = Pair<bf16>::pack(v[j + 6], v[j + 7]);
-            *reinterpret_cast<uint4*>(tile_smem + lane * 64 + ((j4 ^ sw) << 4)) = q;
+            // planar output: the staging tile is [4 channel groups][32 rows][16 B] (un-swizzled, one 3-D box)
+            *reinterpret_cast<uint4*>(g.out_gp ? tile_smem + j4 * 512 + lane * 16 : tile_smem + lane * 64 + ((j4 ^ sw) << 4)) = q;
           }
           ptx::fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
-            ptx::tma_store_2d(&tmOut, tile_smem, n, row0);
+            if (g.out_gp) ptx::tma_store_3d(&tmOut, tile_smem, 0, row0 >> 5, n >> 3);
+            else ptx::tma_store_2d(&tmOut, tile_smem, n, row0);
             ptx::tma_store_commit();
           }
           store_parity ^= 1;
@@ -334,7 +370,7 @@ static int launch_umma_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, cons
   using Cfg = GemmCfg<BN, NEPI, CG>;
   auto kern = umma_gemm_kernel<BN, EPI, NEPI, CG>;
   ACX_SET_MAX_SMEM(kern, Cfg::SMEM_BYTES);
-  ACX_CHECK(g.N * (EPI == ACX_EPI_BIAS_SCALE_RESID ? 8 : 4) <= Cfg::VEC_BYTES, ACX_ERR_UNSUPPORTED,
+  ACX_CHECK(g.N * (EPI == ACX_EPI_BIAS_SCALE_RESID || EPI == ACX_EPI_BIAS_GELU_FOLD ? 8 : 4) <= Cfg::VEC_BYTES, ACX_ERR_UNSUPPORTED,
             "gemm_bf16: N=%d exceeds the per-column vectors staged in shared memory", g.N);
   int dev = 0, sms = 0;
   ACX_CUDA(cudaGetDevice(&dev));
@@ -386,8 +422,9 @@ static int dispatch_bn(const CUtensorMap& tmA, const void* W, const GemmArgs& g,
   if (rc != ACX_OK) return rc;
   // output: 32-column x 32-row boxes (one per epilogue warp and chunk), 64B swizzle
   CUtensorMap tmOut;
-  rc = make_tmap_2d_bf16(&tmOut, g.out, (uint64_t)g.N, (uint64_t)g.M, (uint64_t)g.N * 2, 32, 32,
-                         CU_TENSOR_MAP_SWIZZLE_64B);
+  rc = g.out_gp ? make_tmap_gp_bf16(&tmOut, g.out, (uint64_t)g.M, (uint64_t)g.N / 8, 32, 4)
+                : make_tmap_2d_bf16(&tmOut, g.out, (uint64_t)g.N, (uint64_t)g.M, (uint64_t)g.N * 2, 32, 32,
+                                    CU_TENSOR_MAP_SWIZZLE_64B);
   if (rc != ACX_OK) return rc;
   if (pair) {
     if (bn == 256) return launch_umma_gemm<256, EPI, 8, 2>(tmA, tmB, tmOut, g, st);
@@ -405,8 +442,9 @@ static int dispatch_bn(const CUtensorMap& tmA, const void* W, const GemmArgs& g,
 
 using namespace acx;
 
-extern "C" int acx_gemm_bf16(const void* A, const void* W, void* out, int M, int N, int K, int epilogue,
-                             const float* bias, const float* gamma, const void* resid, void* stream) {
+static int gemm_bf16_impl(const void* A, const void* W, void* out, int M, int N, int K, int epilogue, const float* bias,
+                          const float* gamma, const void* resid, int out_gp, int a_gp, const float* stats,
+                          const float* ln_s, void* stream) {
   ACX_CHECK(A && W && out && bias, ACX_ERR_ARG, "gemm_bf16: null pointer (A, W, out and bias are required)");
   ACX_CHECK(M > 0 && N > 0 && K > 0 && K % 8 == 0, ACX_ERR_ARG, "gemm_bf16: K=%d must be a positive multiple of 8", K);
   ACX_CHECK((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0 &&
@@ -414,6 +452,10 @@ extern "C" int acx_gemm_bf16(const void* A, const void* W, void* out, int M, int
             ACX_ERR_ARG, "gemm_bf16: A, W and out must be 16-byte aligned");
   if (epilogue == ACX_EPI_BIAS_SCALE_RESID)
     ACX_CHECK(gamma && resid, ACX_ERR_ARG, "gemm_bf16: scale+residual epilogue needs gamma and resid");
+  ACX_CHECK(!out_gp || epilogue != ACX_EPI_BIAS_GELU, ACX_ERR_UNSUPPORTED, "gemm_bf16: the hidden activation stays row-major");
+  ACX_CHECK(!a_gp || K % 64 == 0, ACX_ERR_UNSUPPORTED, "gemm_bf16: a planar A operand needs K %% 64 == 0 (got %d)", K);
+  ACX_CHECK((stats == nullptr) == (ln_s == nullptr), ACX_ERR_ARG, "gemm_bf16: stats and ln_s go together");
+  ACX_CHECK(!stats || epilogue == ACX_EPI_BIAS_GELU, ACX_ERR_UNSUPPORTED, "gemm_bf16: the LayerNorm fold belongs to the GELU epilogue");
   GemmArgs g;
   g.out = reinterpret_cast<bf16*>(out);
   g.bias = bias;
@@ -422,16 +464,48 @@ extern "C" int acx_gemm_bf16(const void* A, const void* W, void* out, int M, int
   g.M = M;
   g.N = N;
   g.K = K;
+  g.out_gp = out_gp;
+  g.a_gp = a_gp;
+  g.stats = reinterpret_cast<const float2*>(stats);
+  g.ln_s = ln_s;
   CUtensorMap tmA;
-  int rc = make_tmap_2d_bf16(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)K * 2, 64, 128);
+  int rc = a_gp ? make_tmap_gp_bf16(&tmA, A, (uint64_t)M, (uint64_t)K / 8, 128, 8)
+                : make_tmap_2d_bf16(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)K * 2, 64, 128);
   if (rc != ACX_OK) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   switch (epilogue) {
     case ACX_EPI_BIAS: return dispatch_bn<ACX_EPI_BIAS>(tmA, W, g, st);
-    case ACX_EPI_BIAS_GELU: return dispatch_bn<ACX_EPI_BIAS_GELU>(tmA, W, g, st);
+    case ACX_EPI_BIAS_GELU:
+      return stats ? dispatch_bn<ACX_EPI_BIAS_GELU_FOLD>(tmA, W, g, st) : dispatch_bn<ACX_EPI_BIAS_GELU>(tmA, W, g, st);
     case ACX_EPI_BIAS_SCALE_RESID: return dispatch_bn<ACX_EPI_BIAS_SCALE_RESID>(tmA, W, g, st);
     default:
       set_error("gemm_bf16: unknown epilogue %d", epilogue);
       return ACX_ERR_ARG;
   }
+}
+
+extern "C" int acx_gemm_bf16(const void* A, const void* W, void* out, int M, int N, int K, int epilogue,
+                             const float* bias, const float* gamma, const void* resid, void* stream) {
+  return gemm_bf16_impl(A, W, out, M, N, K, epilogue, bias, gamma, resid, 0, 0, nullptr, nullptr, stream);
+}
+
+// out = A . W^T + bias written GROUP-PLANAR, [N/8][Mp][8] (Mp = M rounded up to 128): the downsample GEMM in front of a
+// stage whose depthwise conv runs on the tensor cores hands over in that layout instead of a transpose pass.
+extern "C" int acx_gemm_bf16_gp_out(const void* A, const void* W, void* out, int M, int N, int K, const float* bias,
+                                    void* stream) {
+  return gemm_bf16_impl(A, W, out, M, N, K, ACX_EPI_BIAS, bias, nullptr, nullptr, 1, 0, nullptr, nullptr, stream);
+}
+
+// The two GEMMs of a Block MLP on group-planar activations (stages whose MLP is not the fused kernel):
+//   pwconv1: hid = GELU( LN(v) . W1^T + b1 ) with v planar [C/8][Mp][8], the LayerNorm folded (w1 = bf16(W1 ln_w),
+//            b1 = b1 + W1 ln_b, ln_s = row sums of w1, stats = acx_gp_row_stats(v)); hid row-major (M, 4C);
+//   pwconv2: x += gamma * (hid . W2^T + b2) with x planar, updated in place.
+extern "C" int acx_gemm_bf16_pw1_gp(const void* v_gp, const void* w1f, void* hid, int M, int N, int K, const float* b1f,
+                                    const float* stats, const float* ln_s, void* stream) {
+  ACX_CHECK(stats && ln_s, ACX_ERR_ARG, "gemm_bf16_pw1_gp: stats and ln_s are required");
+  return gemm_bf16_impl(v_gp, w1f, hid, M, N, K, ACX_EPI_BIAS_GELU, b1f, nullptr, nullptr, 0, 1, stats, ln_s, stream);
+}
+extern "C" int acx_gemm_bf16_pw2_gp(const void* hid, const void* w2, void* x_gp, int M, int N, int K, const float* b2,
+                                    const float* gamma, void* stream) {
+  return gemm_bf16_impl(hid, w2, x_gp, M, N, K, ACX_EPI_BIAS_SCALE_RESID, b2, gamma, x_gp, 1, 0, nullptr, nullptr, stream);
 }

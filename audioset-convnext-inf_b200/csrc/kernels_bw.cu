@@ -883,8 +883,8 @@ int acx_ln_patchify(const void* x, const float* ln_w, const float* ln_b, void* a
 int acx_ln_patchify_gp(const void* x, const float* ln_w, const float* ln_b, void* a, int B, int H, int W, int C,
                        void* stream) {
   ACX_CHECK(x && ln_w && ln_b && a, ACX_ERR_ARG, "ln_patchify_gp: null pointer");
-  ACX_CHECK((C == 96 || C == 192) && H >= 2 && W >= 2, ACX_ERR_ARG,
-            "ln_patchify_gp: unsupported shape C=%d H=%d W=%d (C must be 96 or 192)", C, H, W);
+  ACX_CHECK((C == 96 || C == 192 || C == 384) && H >= 2 && W >= 2, ACX_ERR_ARG,
+            "ln_patchify_gp: unsupported shape C=%d H=%d W=%d (C must be 96, 192 or 384)", C, H, W);
   const long long total = (long long)B * (H / 2) * 2 * (W / 2) * 2;
   const long long lanes = (total + 1) / 2 * (C / 24);
   const int blocks = (int)((lanes + 255) / 256);
@@ -892,8 +892,11 @@ int acx_ln_patchify_gp(const void* x, const float* ln_w, const float* ln_b, void
   if (C == 96)
     ln_patchify_kernel<bf16, 96, true><<<blocks, 256, 0, st>>>(reinterpret_cast<const bf16*>(x), ln_w, ln_b,
                                                                reinterpret_cast<bf16*>(a), B, H, W);
-  else
+  else if (C == 192)
     ln_patchify_kernel<bf16, 192, true><<<blocks, 256, 0, st>>>(reinterpret_cast<const bf16*>(x), ln_w, ln_b,
+                                                                reinterpret_cast<bf16*>(a), B, H, W);
+  else
+    ln_patchify_kernel<bf16, 384, true><<<blocks, 256, 0, st>>>(reinterpret_cast<const bf16*>(x), ln_w, ln_b,
                                                                 reinterpret_cast<bf16*>(a), B, H, W);
   ACX_CUDA(cudaGetLastError());
   return ACX_OK;

@@ -114,7 +114,7 @@ class PackedWeights:
                     w1=g(p + "pwconv1.weight").to(adt).contiguous(), b1=g(p + "pwconv1.bias").contiguous(),
                     w2=g(p + "pwconv2.weight").to(adt).contiguous(), b2=g(p + "pwconv2.bias").contiguous(),
                     gamma=g(p + "gamma").contiguous()))
-                if precision == "bf16" and s < 2:
+                if precision == "bf16" and s < 3:
                     stage[-1].update(fold_layernorm_into_pwconv1(g(p + "pwconv1.weight"), g(p + "pwconv1.bias"),
                                                                  g(p + "norm.weight"), g(p + "norm.bias")))
             self.blocks.append(stage)
@@ -176,7 +176,7 @@ class Engine:
         # depthwise 7x7: "tc" = banded-Toeplitz tcgen05 GEMMs (dwconv_tc.cu) + LayerNorm pass, "simt" = CUDA-core kernel
         # with the LayerNorm fused; ACX_DWCONV_TC_STAGES picks the stages that take the tensor-core route
         self.dwconv = os.environ.get("ACX_DWCONV", "tc" if precision == "bf16" else "simt")
-        self.dwconv_tc_stages = tuple(int(c) for c in os.environ.get("ACX_DWCONV_TC_STAGES", "01"))
+        self.dwconv_tc_stages = tuple(int(c) for c in os.environ.get("ACX_DWCONV_TC_STAGES", "012"))
         # stages 0 / 1 with the fused MLP keep their activations GROUP-PLANAR ([C/8][M][8]) between the stage's entry
         # and its downsample layer: the tensor-core conv then moves whole cache lines (dwconv_tc.cu); ACX_GP=0 keeps NHWC
         self.gp = os.environ.get("ACX_GP", "1") == "1"
@@ -220,7 +220,8 @@ class Engine:
         ws["y"] = torch.empty(m0 * DIMS[0] + pad, device=dev, dtype=adt)
         ws["hid"] = torch.empty(m0 * 4 * DIMS[0], device=dev, dtype=adt)
         if self.precision == "bf16":
-            ws["xg"] = torch.empty(m0 * DIMS[0] + pad, device=dev, dtype=adt)      # group-planar residual stream (stages 0 / 1)
+            ws["xg"] = torch.empty(m0 * DIMS[0] + pad, device=dev, dtype=adt)      # group-planar residual stream (stages 0 - 2)
+            ws["stats"] = torch.empty(n * hs[2] * 14 + 128, 2, device=dev, dtype=torch.float32)   # stage 2: per-row (rstd, -mean rstd)
         ws["pooled"] = torch.empty(n, DIMS[3], device=dev, dtype=torch.float32)
         # static outputs so that a captured CUDA graph can be replayed for any caller-owned output tensor
         ws["scene"] = torch.empty(n, DIMS[3], device=dev, dtype=torch.float32)
@@ -279,6 +280,10 @@ class Engine:
             C = int(tag[len("mlp_fused_c"):])
             s = DIMS.index(C)
             return "tensor", 2.0 * (n * hs[s] * (56 >> s)) * C * 4 * C * 2
+        if tag.startswith("row_stats_c"):
+            C = int(tag.rsplit("_c", 1)[1])
+            s = DIMS.index(C)
+            return "hbm", 1.0 * n * hs[s] * (56 >> s) * C * es
         if tag.startswith(("dwconv_tc_c", "ln_rows_c", "to_gp_c")):
             C = int(tag.rsplit("_c", 1)[1])
             s = DIMS.index(C)
@@ -348,18 +353,32 @@ class Engine:
             self._call("stem", "acx_stem", ws["logmel"].data_ptr(), w.stem_w.data_ptr(), w.stem_b.data_ptr(),
                        w.stem_ln_w.data_ptr(), w.stem_ln_b.data_ptr(), x, n, ws["T"], N_MELS, self.adt, st)
         Wd = 56
+        entered_gp = False          # the previous downsample GEMM already wrote this stage's planar input
         for s in range(4):
             C, H = DIMS[s], ws["hs"][s]
             M = n * H * Wd
             fused_mlp = self.mlp == "fused" and C in (96, 192)
             tc = self.dwconv == "tc" and s in self.dwconv_tc_stages
             gp = tc and fused_mlp and self.gp and Wd in (56, 28)
-            if gp:
+            gp2 = tc and not fused_mlp and self.gp and self.mlp == "fused" and Wd == 14 and C == 384   # planar, two-GEMM MLP
+            if gp2:
+                xg, vg = ws["xg"].data_ptr(), y
+                if not entered_gp:
+                    self._call(f"to_gp_c{C}", "acx_gp_transpose", x, xg, M, C, 1, st)
+                stats = ws["stats"].data_ptr()
+                for blk in w.blocks[s]:
+                    self._call(f"dwconv_tc_c{C}", "acx_dwconv_tc_gp", xg, blk["dw_w"].data_ptr(), blk["dw_b"].data_ptr(), vg, n, H, Wd, C, st)
+                    self._call(f"row_stats_c{C}", "acx_gp_row_stats", vg, stats, M, C, st)
+                    self._call(f"pw1_gelu_k{C}_n{4 * C}", "acx_gemm_bf16_pw1_gp", vg, blk["w1f"].data_ptr(), hid, M, 4 * C, C,
+                               blk["b1f"].data_ptr(), stats, blk["s1"].data_ptr(), st)
+                    self._call(f"pw2_resid_k{4 * C}_n{C}", "acx_gemm_bf16_pw2_gp", hid, blk["w2"].data_ptr(), xg, M, C, 4 * C,
+                               blk["b2"].data_ptr(), blk["gamma"].data_ptr(), st)
+            elif gp:
                 # group-planar residual stream for this stage: xg <- x; the row-major x buffer becomes the conv output
                 xg, vg = ws["xg"].data_ptr(), x
-                if not (s == 0 and stem_gp):
+                if not (s == 0 and stem_gp) and not entered_gp:
                     self._call(f"to_gp_c{C}", "acx_gp_transpose", x, xg, M, C, 1, st)
-            for blk in w.blocks[s]:
+            for blk in (() if gp2 else w.blocks[s]):
                 if gp:
                     self._call(f"dwconv_tc_c{C}", "acx_dwconv_tc_gp", xg, blk["dw_w"].data_ptr(), blk["dw_b"].data_ptr(), vg, n, H, Wd, C, st)
                     # the LayerNorm runs inside the MLP kernel: folded into pwconv1 as a rank-1 epilogue correction
@@ -395,13 +414,21 @@ class Engine:
                                blk["b2"].data_ptr(), blk["gamma"].data_ptr(), x, st)
             if s < 3:
                 d = w.ds[s]
-                if gp:
+                if gp or gp2:
                     self._call(f"ln_patchify_c{C}", "acx_ln_patchify_gp", xg, d["ln_w"].data_ptr(), d["ln_b"].data_ptr(), y, n, H, Wd, C, st)
                 else:
                     self._call(f"ln_patchify_c{C}", "acx_ln_patchify", x, d["ln_w"].data_ptr(), d["ln_b"].data_ptr(), y, n, H, Wd, C, self.adt, st)
                 Wd //= 2
                 Mo = n * ws["hs"][s + 1] * Wd
-                self._gemm(y, d["w"].data_ptr(), x, Mo, 2 * C, 4 * C, N.EPI_BIAS, d["b"].data_ptr(), 0, 0, st)
+                # the next stage takes its input group-planar: the downsample GEMM writes that layout itself
+                entered_gp = (self.precision == "bf16" and self.mlp == "fused" and 2 * C in (96, 192, 384) and self.dwconv == "tc"
+                              and (s + 1) in self.dwconv_tc_stages and self.gp and Wd in (56, 28, 14)
+                              and os.environ.get("ACX_DS_GP", "1") == "1")
+                if entered_gp:
+                    self._call(f"ds_k{4 * C}_n{2 * C}", "acx_gemm_bf16_gp_out", y, d["w"].data_ptr(), ws["xg"].data_ptr(), Mo, 2 * C, 4 * C,
+                               d["b"].data_ptr(), st)
+                else:
+                    self._gemm(y, d["w"].data_ptr(), x, Mo, 2 * C, 4 * C, N.EPI_BIAS, d["b"].data_ptr(), 0, 0, st)
 
     def _body(self, ws, n, L, st, trunk, need_head, need_frame):
         """Everything after wave_prep for one chunk; writes only into the workspace (graph-capturable)."""

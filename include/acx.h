@@ -115,6 +115,8 @@ ACX_API int acx_layernorm_rows(const void* in, const float* ln_w, const float* l
 ACX_API int acx_dwconv_tc_gp(const void* x, const void* w, const float* bias, void* v, int B, int H, int W, int C,
                      void* stream);
 ACX_API int acx_gp_transpose(const void* in, void* out, long long M, int C, int to_gp, void* stream);
+/* stats[row] = (rstd, -mean * rstd) of the C channels of each row of a group-planar tensor (LayerNorm eps 1e-6) */
+ACX_API int acx_gp_row_stats(const void* v, float* stats, long long M, int C, void* stream);
 
 /* ---- downsample prologue: channels_first LayerNorm + 2x2/s2 patch gather (CX:231-234) ------- */
 /* x (B,H,W,C) -> a (B*(H/2)*(W/2), 4C) with k = (dy*2+dx)*C + c  (the GEMM A operand). */
@@ -128,6 +130,17 @@ ACX_API int acx_ln_patchify_gp(const void* x, const float* ln_w, const float* ln
 /* bf16 operands, fp32 accumulation in TMEM (tcgen05.mma, TMA-fed).  K % 8 == 0, N % 32 == 0. */
 ACX_API int acx_gemm_bf16(const void* A, const void* W, void* out, int M, int N, int K, int epilogue,
                   const float* bias, const float* gamma, const void* resid, void* stream);
+/* out = A . W^T + bias written group-planar, [N/8][Mp][8] with Mp = M rounded up to 128 (bias epilogue only) */
+ACX_API int acx_gemm_bf16_gp_out(const void* A, const void* W, void* out, int M, int N, int K, const float* bias,
+                         void* stream);
+/* The two GEMMs of a Block MLP on group-planar activations (stage 2, whose MLP is not the fused kernel):
+ *   pw1: hid (M, N = 4C) row-major = GELU(LN(v) . W1^T + b1), v planar [K/8][Mp][8], LayerNorm folded: w1f = bf16(W1 ln_w),
+ *        b1f = b1 + W1 ln_b, ln_s[j] = sum_k w1f[j, k], stats = acx_gp_row_stats(v);
+ *   pw2: x (planar [N/8][Mp][8], in place) += gamma * (hid . W2^T + b2). */
+ACX_API int acx_gemm_bf16_pw1_gp(const void* v_gp, const void* w1f, void* hid, int M, int N, int K, const float* b1f,
+                         const float* stats, const float* ln_s, void* stream);
+ACX_API int acx_gemm_bf16_pw2_gp(const void* hid, const void* w2, void* x_gp, int M, int N, int K, const float* b2,
+                         const float* gamma, void* stream);
 /* fp32 SIMT GEMM of the fp32-accurate path.  Row m of A starts at
  * A + (m / rows_per_batch) * batch_stride + (m % rows_per_batch) * row_stride (elements), which
  * also expresses the overlapping STFT frames (row_stride = hop). */

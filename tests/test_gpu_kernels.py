@@ -184,7 +184,8 @@ def test_dwconv_tc_then_layernorm_rows(sd, stage, H, B):
     assert torch.equal(v, y)
 
 
-@pytest.mark.parametrize("stage,H,B", [(0, 13, 2), (0, 252, 3), (0, 130, 2), (1, 126, 2), (1, 9, 3), (1, 64, 1)])
+@pytest.mark.parametrize("stage,H,B", [(0, 13, 2), (0, 252, 3), (0, 130, 2), (1, 126, 2), (1, 9, 3), (1, 64, 1), (2, 63, 3),
+                                       (2, 64, 2), (2, 6, 1)])
 def test_dwconv_tc_group_planar(sd, stage, H, B):
     """acx_dwconv_tc_gp on the group-planar hand-off layout [C/8][B*H*W][8] (stages 0 / 1): bit-identical to the NHWC
     kernel (same MMAs, only the addressing differs), exact against F.conv2d up to the bf16 rounding of the result;

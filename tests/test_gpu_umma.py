@@ -254,6 +254,76 @@ def test_mlp_fused_group_planar_folded_layernorm(C, M):
     assert rc != 0 and "excludes" in N.last_error()
 
 
+@pytest.mark.parametrize("M,Nn,K", [(64 * 126 * 28, 192, 384), (300, 192, 384), (128 * 5 + 17, 96, 64)])
+def test_gemm_planar_output_equals_row_major(M, Nn, K):
+    """acx_gemm_bf16_gp_out (the downsample GEMM handing its result over group-planar) == acx_gemm_bf16 + layout change."""
+    g = torch.Generator().manual_seed(M + Nn)
+    a = torch.randn(M, K, generator=g).to(torch.bfloat16).to(DEV)
+    w = (torch.randn(Nn, K, generator=g) / K ** 0.5).to(torch.bfloat16).to(DEV)
+    b = (torch.randn(Nn, generator=g) * 0.1).to(DEV)
+    st = torch.cuda.current_stream().cuda_stream
+    out = torch.empty(M, Nn, device=DEV, dtype=torch.bfloat16)
+    N.call("acx_gemm_bf16", a.data_ptr(), w.data_ptr(), out.data_ptr(), M, Nn, K, N.EPI_BIAS, b.data_ptr(), 0, 0, st)
+    Mp = (M + 127) // 128 * 128
+    og = torch.zeros(Nn // 8, Mp, 8, device=DEV, dtype=torch.bfloat16)
+    N.call("acx_gemm_bf16_gp_out", a.data_ptr(), w.data_ptr(), og.data_ptr(), M, Nn, K, b.data_ptr(), st)
+    torch.cuda.synchronize()
+    assert torch.equal(_from_gp(og, M, Nn), out)
+
+
+@pytest.mark.parametrize("M", [64 * 63 * 14, 3 * 63 * 14, 200])
+def test_stage2_planar_two_gemm_mlp(M):
+    """Stage 2 on group-planar activations: acx_gp_row_stats + acx_gemm_bf16_pw1_gp (planar A operand, LayerNorm folded
+    into the GELU epilogue) + acx_gemm_bf16_pw2_gp (planar residual / output, in place) against an fp64 evaluation of
+    CX:78-86 and against the row-major kernels fed with an explicitly normalised operand."""
+    from audioset_convnext_inf_b200.engine import fold_layernorm_into_pwconv1
+    C = 384
+    g = torch.Generator().manual_seed(M)
+    v = (torch.randn(M, C, generator=g) * (torch.rand(M, 1, generator=g) * 2 + 0.2) + torch.randn(M, 1, generator=g) * 3).to(torch.bfloat16)
+    x = torch.randn(M, C, generator=g).to(torch.bfloat16)
+    w1 = torch.randn(4 * C, C, generator=g) / C ** 0.5
+    w2 = (torch.randn(C, 4 * C, generator=g) / (4 * C) ** 0.5).to(torch.bfloat16)
+    b1 = torch.randn(4 * C, generator=g) * 0.1
+    b2 = torch.randn(C, generator=g) * 0.1
+    gamma = torch.rand(C, generator=g) * 0.5 + 0.1
+    lw = torch.rand(C, generator=g) * 0.4 + 0.8
+    lb = torch.randn(C, generator=g) * 0.05
+    f = fold_layernorm_into_pwconv1(w1, b1, lw, lb)
+    vd, xd, w2d, b2d, gd, lwd, lbd, b1d = (t.to(DEV) for t in (v, x, w2, b2, gamma, lw, lb, b1))
+    w1f, s1, b1f = (f[k].to(DEV) for k in ("w1f", "s1", "b1f"))
+    st = torch.cuda.current_stream().cuda_stream
+    v_gp, x_gp = _to_gp(vd), _to_gp(xd)
+    stats = torch.empty(M, 2, device=DEV)
+    N.call("acx_gp_row_stats", v_gp.data_ptr(), stats.data_ptr(), M, C, st)
+    mean = vd.double().mean(1)
+    rstd = 1.0 / torch.sqrt(vd.double().var(1, unbiased=False) + 1e-6)
+    assert (stats[:, 0].double() - rstd).abs().max().item() < 1e-4 * rstd.max().item()
+    assert (stats[:, 1].double() + mean * rstd).abs().max().item() < 1e-3
+    hid = torch.empty(M, 4 * C, device=DEV, dtype=torch.bfloat16)
+    N.call("acx_gemm_bf16_pw1_gp", v_gp.data_ptr(), w1f.data_ptr(), hid.data_ptr(), M, 4 * C, C, b1f.data_ptr(), stats.data_ptr(),
+           s1.data_ptr(), st)
+    N.call("acx_gemm_bf16_pw2_gp", hid.data_ptr(), w2d.data_ptr(), x_gp.data_ptr(), M, C, 4 * C, b2d.data_ptr(), gd.data_ptr(), st)
+    torch.cuda.synchronize()
+    yn = F.layer_norm(vd.double(), (C,), lwd.double(), lbd.double(), 1e-6)
+    href = F.gelu(yn @ w1.double().to(DEV).t() + b1d.double())
+    assert (hid.double() - href).abs().max().item() < 0.03 + 0.01 * href.abs().max().item()
+    ref = xd.double() + gd.double() * (href @ w2d.double().t() + b2d.double())
+    got = _from_gp(x_gp, M, C)
+    assert torch.isfinite(got.float()).all()
+    assert (got.double() - ref).abs().max().item() < 0.05 + 0.01 * ref.abs().max().item()
+    # row-major path on an explicitly normalised operand (what stage 2 ran before): same result up to bf16 roundings
+    y = torch.empty_like(vd)
+    N.call("acx_layernorm_rows", vd.data_ptr(), lwd.data_ptr(), lbd.data_ptr(), y.data_ptr(), M, C, st)
+    hid2 = torch.empty_like(hid)
+    x2 = xd.clone()
+    w1d = w1.to(torch.bfloat16).to(DEV)
+    N.call("acx_gemm_bf16", y.data_ptr(), w1d.data_ptr(), hid2.data_ptr(), M, 4 * C, C, N.EPI_BIAS_GELU, b1d.data_ptr(), 0, 0, st)
+    N.call("acx_gemm_bf16", hid2.data_ptr(), w2d.data_ptr(), x2.data_ptr(), M, C, 4 * C, N.EPI_BIAS_SCALE_RESID, b2d.data_ptr(),
+           gd.data_ptr(), x2.data_ptr(), st)
+    torch.cuda.synchronize()
+    assert (got.double() - x2.double()).abs().max().item() < 0.06
+
+
 def test_mlp_fused_rejects_wide_stages():
     t = torch.zeros(128, 384, device=DEV, dtype=torch.bfloat16)
     f = torch.zeros(1536, device=DEV)
