@@ -362,8 +362,12 @@ __global__ void __launch_bounds__(THREADS, 1)
                       bf16* __restrict__ v, int n_clips, int H, int C, long long* __restrict__ trace) {
   constexpr int NHALF = W > 32 ? 2 : 1;
   constexpr int HW = NHALF == 2 ? 28 : W;
-  constexpr int KS = W <= 16 ? 1 : 2;           // K steps per (channel, dy): a 14-wide row fits ONE 16-column K window
-  constexpr int NMI = W <= 16 ? 2 : 4;          // 8-pixel blocks per row that can hold image columns
+  // W = 14: an item takes the rows of TWO clips side by side in one 32-column K window -- clip A in columns 0..13, three
+  // zero columns (the conv's own padding, so the band couples nothing across them), clip B in columns 17..30 -- because
+  // an item's cost is mostly fixed hand-offs (a 14-wide item alone took as long as a 28-wide one: 56 us per layer)
+  constexpr bool PAIR = W == 14;
+  constexpr int KS = 2;                         // K steps per (channel, dy)
+  constexpr int NMI = 4;                        // 8-pixel blocks per A row
 #ifdef ACX_ENABLE_TRACE
   long long tr_wait = 0, tr_wait2 = 0, tr_work = 0, tr_t = 0, tr_n = 0;
 #define V3_T0() do { if (trace) tr_t = clock64(); } while (0)
@@ -387,7 +391,7 @@ __global__ void __launch_bounds__(THREADS, 1)
   const int g = blockIdx.x % G, rank = blockIdx.x / G;
   const int ng = ((int)gridDim.x - g + G - 1) / G;            // CTAs that own this channel group
   const int tiles = (H + TR - 1) / TR;
-  const int items = n_clips * tiles * NHALF;
+  const int items = (PAIR ? (n_clips + 1) / 2 : n_clips) * tiles * NHALF;
   const int c0 = g * CG;
   const size_t mtot = ((size_t)n_clips * H * W + 127) / 128 * 128;   // plane stride: rows rounded up to 128
 
@@ -407,14 +411,17 @@ __global__ void __launch_bounds__(THREADS, 1)
     ptx::tmem_alloc(tmem_slot, 512);
     ptx::tmem_relinquish();
   }
+  // the 8 channels' 49 taps first (49 coalesced 16-byte loads into the still unused staging area): building the bands
+  // straight from global memory cost ~25 dependent L2 round trips per thread, 8 us of a 40 us stage-2 launch
+  uint16_t* taps_s = reinterpret_cast<uint16_t*>(smem + OFF_STG);          // [49][8]
+  if (tid < 49) reinterpret_cast<uint4*>(taps_s)[tid] = __ldg(reinterpret_cast<const uint4*>(taps + (size_t)tid * C + c0));
   __syncthreads();
   for (int i = tid; i < CG * 49 * 32; i += THREADS) {          // (channel, tap, n): T[n][k = n + dx - 3] = tap[dy][dx]
     const int n = i & 31, tap = (i >> 5) % 49, c = i / (49 * 32);
     const int dy = tap / 7, dx = tap - dy * 7, k = n + dx - 3;
     if (k >= 0 && k < 32)
       *reinterpret_cast<uint16_t*>(smem + OFF_BANDS + (c * 7 + dy) * BAND_TILE + n * 64 +
-                                   ((((k >> 3) ^ ((n >> 1) & 3)) << 4) + ((k & 7) << 1))) =
-          reinterpret_cast<const uint16_t*>(taps)[tap * C + c0 + c];
+                                   ((((k >> 3) ^ ((n >> 1) & 3)) << 4) + ((k & 7) << 1))) = taps_s[tap * 8 + c];
   }
   ptx::fence_proxy_async_smem();
   ptx::tc_fence_before();
@@ -469,13 +476,14 @@ __global__ void __launch_bounds__(THREADS, 1)
     const bf16* xg = x + (size_t)g * mtot * 8 + 2 * (lane & 3);
     uint32_t it = 0;
     for (int item = rank; item < items; item += ng, ++it) {
-      const int half = item % NHALF, t = (item / NHALF) % tiles, n = item / (NHALF * tiles);
+      const int half = item % NHALF, t = (item / NHALF) % tiles, n = (item / (NHALF * tiles)) * (PAIR ? 2 : 1);
       const int h0 = t * TR, kw0 = half ? 24 : 0;
       const int buf = it & 1;
       V3_T0();
       ptx::mbar_wait(&a_empty[buf], ((it >> 1) & 1) ^ 1);
       V3_ACC(tr_wait);
       const bf16* xin = xg + ((size_t)n * H * W + kw0) * 8;
+      const bool b_ok = PAIR && n + 1 < n_clips;        // the pair's second clip exists
       const uint32_t abuf = s_base + OFF_A + buf * A_BUF;
       constexpr int RPR = (AR + NLOAD - 1) / NLOAD;     // rows per warp: all requested at once
 #pragma unroll 1
@@ -488,7 +496,14 @@ __global__ void __launch_bounds__(THREADS, 1)
 #pragma unroll
           for (int mi = 0; mi < 4; ++mi) {
             const int col = kw0 + mi * 8 + px;
-            q[u][mi] = (mi < NMI && row_ok && col < W) ? ldg_nc_u32(xin + ((size_t)h * W + mi * 8 + px) * 8) : 0u;
+            if (PAIR) {
+              const int ca = mi * 8 + px;               // A column: 0..13 clip A, 17..30 clip B
+              const bool in_a = ca < 14, in_b = ca >= 17 && ca < 31 && b_ok;
+              const size_t off = in_a ? ((size_t)h * W + ca) : ((size_t)(H + h) * W + ca - 17);
+              q[u][mi] = (row_ok && (in_a || in_b)) ? ldg_nc_u32(xin + off * 8) : 0u;
+            } else {
+              q[u][mi] = (mi < NMI && row_ok && col < W) ? ldg_nc_u32(xin + ((size_t)h * W + mi * 8 + px) * 8) : 0u;
+            }
           }
         }
 #pragma unroll
@@ -527,7 +542,7 @@ __global__ void __launch_bounds__(THREADS, 1)
     for (int c = 0; c < CG; ++c) bs[c] = sbias[c];
     uint32_t it = 0;
     for (int item = rank; item < items; item += ng, ++it) {
-      const int half = item % NHALF, t = (item / NHALF) % tiles, n = item / (NHALF * tiles);
+      const int half = item % NHALF, t = (item / NHALF) % tiles, n = (item / (NHALF * tiles)) * (PAIR ? 2 : 1);
       const int h0 = t * TR;
       const int buf = it & 1;
       V3_T0();
@@ -556,14 +571,17 @@ __global__ void __launch_bounds__(THREADS, 1)
         for (int e = 0; e < 4; ++e) {
           const int mm = (e & 2) ? m_b : m_a;
           const int col = side * 16 + b * 8 + 2 * (lane & 3) + (e & 1);
-          const bool ok = mm < TR && h0 + mm < H && (half == 0 ? col < HW : col >= 4);
+          // staging slot of this accumulator column: pixel of the half row; PAIR: clip A 0..13, clip B 14..27
+          const int slot = PAIR ? (col < 14 ? col : col - 3) : (half == 0 ? col : col - 4);
+          const bool ok = mm < TR && h0 + mm < H &&
+                          (PAIR ? (col < 14 || (col >= 17 && col < 31)) : (half == 0 ? col < HW : col >= 4));
           if (ok) {
             uint4 o;
             o.x = Pair<bf16>::pack(__uint_as_float(r[b][0][e]) + bs[0], __uint_as_float(r[b][1][e]) + bs[1]);
             o.y = Pair<bf16>::pack(__uint_as_float(r[b][2][e]) + bs[2], __uint_as_float(r[b][3][e]) + bs[3]);
             o.z = Pair<bf16>::pack(__uint_as_float(r[b][4][e]) + bs[4], __uint_as_float(r[b][5][e]) + bs[5]);
             o.w = Pair<bf16>::pack(__uint_as_float(r[b][6][e]) + bs[6], __uint_as_float(r[b][7][e]) + bs[7]);
-            *reinterpret_cast<uint4*>(smem + OFF_STG + mm * STG_PITCH + (half == 0 ? col : col - 4) * 16) = o;
+            *reinterpret_cast<uint4*>(smem + OFF_STG + mm * STG_PITCH + slot * 16) = o;
           }
         }
       }
@@ -574,6 +592,13 @@ __global__ void __launch_bounds__(THREADS, 1)
         bf16* vg = v + ((size_t)g * mtot + ((size_t)n * H + h0 + etid) * W + (half == 0 ? 0 : 28)) * 8;
         asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(vg),
                      "r"(s_base + OFF_STG + etid * STG_PITCH), "n"(HW * 16)
+                     : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      } else if (PAIR && etid >= 64 && etid - 64 < rows && n + 1 < n_clips) {     // the pair's second clip
+        const int row = etid - 64;
+        bf16* vg = v + ((size_t)g * mtot + ((size_t)(n + 1) * H + h0 + row) * W) * 8;
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(vg),
+                     "r"(s_base + OFF_STG + row * STG_PITCH + HW * 16), "n"(HW * 16)
                      : "memory");
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
@@ -600,7 +625,7 @@ static int launch(const void* x, const void* taps, const float* bias, void* v, i
   auto kern = dwconv_tc3_kernel<W>;
   ACX_SET_MAX_SMEM(kern, SMEM_BYTES);
   const int G = C / CG;
-  const long long work = (long long)G * B * ceil_div(H, TR) * (W > 32 ? 2 : 1);
+  const long long work = (long long)G * (W == 14 ? (B + 1) / 2 : B) * ceil_div(H, TR) * (W > 32 ? 2 : 1);
   const int sms = sm_count();
   const int grid = work < sms ? (int)work : sms;       // >= G whenever there is at least one item per group
   long long* trace = nullptr;
@@ -739,8 +764,8 @@ extern "C" int acx_dwconv_tc_gp(const void* x, const void* w, const float* bias,
   ACX_CHECK(B > 0 && H > 0, ACX_ERR_ARG, "dwconv_tc_gp: B and H must be positive");
   ACX_CHECK(C % 8 == 0 && C > 0, ACX_ERR_ARG, "dwconv_tc_gp: C must be a positive multiple of 8 (got %d)", C);
   ACX_CHECK(x != v, ACX_ERR_ARG, "dwconv_tc_gp: out of place only (neighbouring units read the input halo)");
-  ACX_CHECK(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(v)) & 15) == 0, ACX_ERR_ARG,
-            "dwconv_tc_gp: x and v must be 16-byte aligned");
+  ACX_CHECK(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(w)) & 15) == 0,
+            ACX_ERR_ARG, "dwconv_tc_gp: x, v and w must be 16-byte aligned");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   static const bool use_v1 = getenv("ACX_DWTC_V1") != nullptr;      // the two-CTA-per-SM kernel, kept for A/B timing
   switch (W) {
@@ -795,9 +820,9 @@ __global__ void __launch_bounds__(256) gp_transpose_kernel(const uint4* __restri
 // none of them owns the row, so they are computed once here (one pass over v: thread = row, loads coalesced per plane).
 namespace acx {
 namespace dwtc {
-__global__ void __launch_bounds__(256) gp_row_stats_kernel(const uint4* __restrict__ v, float2* __restrict__ stats,
+__global__ void __launch_bounds__(128) gp_row_stats_kernel(const uint4* __restrict__ v, float2* __restrict__ stats,
                                                            long long M, int G) {
-  const long long row = (long long)blockIdx.x * 256 + threadIdx.x;
+  const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= M) return;
   const long long Mp = (M + 127) / 128 * 128;
   const float inv_c = 1.0f / (8.0f * G);
@@ -805,15 +830,21 @@ __global__ void __launch_bounds__(256) gp_row_stats_kernel(const uint4* __restri
   const float shift = __uint_as_float(first.x << 16);
   const float2 sh2 = make_float2(-shift, -shift);
   float2 s = make_float2(0.f, 0.f), q = make_float2(0.f, 0.f);
-#pragma unroll 4
-  for (int gq = 0; gq < G; ++gq) {
-    const uint4 u = __ldg(v + (long long)gq * Mp + row);
-    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+  for (int g0 = 0; g0 < G; g0 += 12) {            // 12 independent 16-byte loads in flight per thread
+    uint4 u[12];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float2 d = __fadd2_rn(Pair<bf16>::unpack(w[k]), sh2);
-      s = __fadd2_rn(s, d);
-      q = __ffma2_rn(d, d, q);
+    for (int j = 0; j < 12; ++j) u[j] = g0 + j < G ? __ldg(v + (long long)(g0 + j) * Mp + row) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+    for (int j = 0; j < 12; ++j) {
+      if (g0 + j < G) {
+        const uint32_t w[4] = {u[j].x, u[j].y, u[j].z, u[j].w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 d = __fadd2_rn(Pair<bf16>::unpack(w[k]), sh2);
+          s = __fadd2_rn(s, d);
+          q = __ffma2_rn(d, d, q);
+        }
+      }
     }
   }
   const float md = (s.x + s.y) * inv_c;
@@ -827,7 +858,7 @@ __global__ void __launch_bounds__(256) gp_row_stats_kernel(const uint4* __restri
 extern "C" int acx_gp_row_stats(const void* v, float* stats, long long M, int C, void* stream) {
   ACX_CHECK(v && stats, ACX_ERR_ARG, "gp_row_stats: null pointer");
   ACX_CHECK(M > 0 && C > 0 && C % 8 == 0, ACX_ERR_ARG, "gp_row_stats: bad shape M=%lld C=%d", M, C);
-  dwtc::gp_row_stats_kernel<<<(unsigned)((M + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  dwtc::gp_row_stats_kernel<<<(unsigned)((M + 127) / 128), 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const uint4*>(v), reinterpret_cast<float2*>(stats), M, C / 8);
   ACX_CUDA(cudaGetLastError());
   return ACX_OK;
