@@ -393,3 +393,27 @@ def test_amplitude_contract_check_is_opt_in(models, monkeypatch):
     ref = O.forward((w * 300.0).cpu(), weights.make_state_dict("parity", 8))["clipwise_logits"]
     got = models["fp32"](w * 300.0)["clipwise_logits"].cpu()
     assert (got - ref).abs().max() < 5e-4
+
+
+@pytest.mark.parametrize("env", [{"ACX_DWCONV": "simt"}, {"ACX_GP": "0"}, {"ACX_LN": "smem"}, {"ACX_DWCONV_TC_STAGES": "0"},
+                                 {"ACX_DS_GP": "0"}])
+def test_alternative_kernel_routes_agree(parity_sd, monkeypatch, env):
+    """Every selectable route of the block -- CUDA-core depthwise conv + fused LayerNorm (round 1), tensor-core conv on
+    row-major tensors, LayerNorm applied in shared memory instead of folded, planar layout in stage 0 only, transpose pass
+    instead of a planar downsample GEMM -- gives the same logits as the default route within the bf16-mode tolerance:
+    the routes differ only in where roundings to bf16 happen."""
+    wave = weights.make_waveforms(2, n_samples=64000, kind="tones", seed=3).to(DEV)
+
+    def run():
+        m = acx.convnext_tiny(pretrained=False, strict=False, drop_path_rate=0.0, after_stem_dim=[252, 56])
+        m.load_state_dict(parity_sd, strict=True)
+        m = m.to(DEV).eval().set_precision("bf16")
+        return m(wave)["clipwise_logits"].cpu()
+
+    base = run()
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    alt = run()
+    ref = O.forward(wave.cpu(), parity_sd)["clipwise_logits"]
+    assert (alt - ref).abs().max().item() < TOL["bf16"]["logits"]
+    assert (alt - base).abs().max().item() < TOL["bf16"]["logits"]
