@@ -34,6 +34,7 @@ SIGNATURES = {
     "acx_gp_row_stats": [_vp, _vp, _ll, _i, _vp],
     "acx_ln_patchify_gp": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "acx_ln_patchify": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
+    "acx_downsample_fused_gp": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     "acx_gemm_bf16": [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp],
     "acx_gemm_bf16_gp_out": [_vp, _vp, _vp, _i, _i, _i, _vp, _vp],
     "acx_gemm_bf16_pw1_gp": [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp],

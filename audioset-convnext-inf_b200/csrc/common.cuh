@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <atomic>
 
@@ -61,6 +62,58 @@ static inline int sm_count() {
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) return 148;
   if (dev < 64) cached[dev].store(sms, std::memory_order_relaxed);
   return sms;
+}
+
+#ifndef ACX_PDL_DEFAULT
+#define ACX_PDL_DEFAULT 7   /* GEMM + fused MLP + tensor-core conv: measured -2 % step time; with the small kernels included the gain is lost (tools/ab_pdl.py) */
+#endif
+// ---- programmatic dependent launch ----------------------------------------------------------------------------------
+// The ~68 kernels of a forward run back to back on one stream.  Launched with the programmatic-stream-serialization
+// attribute, kernel i+1's CTAs are scheduled as soon as every CTA of kernel i has executed pdl_trigger() and an SM has
+// room: their prologue (barrier init, TMEM allocation, weight preload, band build -- nothing that depends on kernel i)
+// runs under kernel i's tail, and they block in pdl_wait() until kernel i has completed and its writes are visible.
+// Rules every kernel on the path follows:
+//   * pdl_trigger() comes AFTER the CTA has acquired everything it will ever need (TMEM): a dependent CTA that became
+//     co-resident earlier could take the TMEM columns this CTA still has to allocate and then wait for it forever;
+//   * pdl_wait() comes before the first access (read OR write) to any buffer another kernel of the stream touches;
+//     only weights / constants may be read above it.
+// Without the attribute (ACX_PDL=0, or a launch that follows a non-kernel stream operation) both are no-ops.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// which launches carry the attribute: ACX_PDL is a bit mask over the kernel families (A/B experiments); 0 = none
+enum PdlKind { PDL_GEMM = 1, PDL_MLP = 2, PDL_DWTC = 4, PDL_STATS = 8, PDL_SMALL = 16 };
+static inline bool pdl_enabled(int kind) {      // read per launch: a captured graph keeps what was set at capture time
+  const char* e = getenv("ACX_PDL");
+  return ((e ? atoi(e) : ACX_PDL_DEFAULT) & kind) != 0;
+}
+
+// cudaLaunchKernelEx with the programmatic-stream-serialization attribute (and optionally a cluster dimension)
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster_x,
+                                     int kind, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  unsigned na = 0;
+  if (cluster_x > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = cluster_x;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (pdl_enabled(kind)) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }

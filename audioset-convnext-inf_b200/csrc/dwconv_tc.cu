@@ -428,6 +428,8 @@ __global__ void __launch_bounds__(THREADS, 1)
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  pdl_trigger();       // TMEM allocated, bands built: everything above read only this layer's taps and bias, so under
+  pdl_wait();          // programmatic dependent launch it overlaps the tail of the kernel that produces x
 
   if (warp == 0) {
     // ===================== MMA issuer ==================================================================================
@@ -632,9 +634,8 @@ static int launch(const void* x, const void* taps, const float* bias, void* v, i
 #ifdef ACX_ENABLE_TRACE
   if (getenv("ACX_DWTC_TRACE")) trace = reinterpret_cast<long long*>(strtoull(getenv("ACX_DWTC_TRACE"), nullptr, 0));
 #endif
-  kern<<<grid, THREADS, SMEM_BYTES, st>>>(reinterpret_cast<const bf16*>(x), reinterpret_cast<const bf16*>(taps), bias,
-                                          reinterpret_cast<bf16*>(v), B, H, C, trace);
-  ACX_CUDA(cudaGetLastError());
+  ACX_CUDA(launch_pdl(kern, dim3(grid), dim3(THREADS), SMEM_BYTES, st, 1, PDL_DWTC, reinterpret_cast<const bf16*>(x),
+                      reinterpret_cast<const bf16*>(taps), bias, reinterpret_cast<bf16*>(v), B, H, C, trace));
   return ACX_OK;
 }
 }  // namespace v3
@@ -822,6 +823,8 @@ namespace acx {
 namespace dwtc {
 __global__ void __launch_bounds__(128) gp_row_stats_kernel(const uint4* __restrict__ v, float2* __restrict__ stats,
                                                            long long M, int G) {
+  pdl_trigger();
+  pdl_wait();
   const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= M) return;
   const long long Mp = (M + 127) / 128 * 128;
@@ -858,9 +861,8 @@ __global__ void __launch_bounds__(128) gp_row_stats_kernel(const uint4* __restri
 extern "C" int acx_gp_row_stats(const void* v, float* stats, long long M, int C, void* stream) {
   ACX_CHECK(v && stats, ACX_ERR_ARG, "gp_row_stats: null pointer");
   ACX_CHECK(M > 0 && C > 0 && C % 8 == 0, ACX_ERR_ARG, "gp_row_stats: bad shape M=%lld C=%d", M, C);
-  dwtc::gp_row_stats_kernel<<<(unsigned)((M + 127) / 128), 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const uint4*>(v), reinterpret_cast<float2*>(stats), M, C / 8);
-  ACX_CUDA(cudaGetLastError());
+  ACX_CUDA(launch_pdl(dwtc::gp_row_stats_kernel, dim3((unsigned)((M + 127) / 128)), dim3(128), 0, reinterpret_cast<cudaStream_t>(stream),
+                      1, PDL_STATS, reinterpret_cast<const uint4*>(v), reinterpret_cast<float2*>(stats), M, C / 8));
   return ACX_OK;
 }
 

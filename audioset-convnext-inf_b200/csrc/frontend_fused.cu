@@ -101,6 +101,8 @@ __global__ void __launch_bounds__(fe::THREADS, 1)
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();       // programmatic dependent launch (common.cuh): resources acquired, dependents may be scheduled
+  pdl_wait();          // the split waveform is wave_prep's output
   uint8_t* sP = smem + OFF_P;
   uint8_t* sMel = smem + OFF_MEL;
 
@@ -318,8 +320,7 @@ extern "C" int acx_frontend_fused(const void* hi, const void* lo, int ld_pad, co
   a.tiles_per_clip = ceil_div(T, fe::BM);
   a.n_mels = n_mels;
   const int grid = B * a.tiles_per_clip;
-  frontend_fused_kernel<<<grid, fe::THREADS, fe::SMEM_BYTES, reinterpret_cast<cudaStream_t>(stream)>>>(
-      tmWavHi, tmWavLo, tmDftHi, tmDftLo, tmMelHi, tmMelLo, a);
-  ACX_CUDA(cudaGetLastError());
+  ACX_CUDA(launch_pdl(frontend_fused_kernel, dim3(grid), dim3(fe::THREADS), fe::SMEM_BYTES, reinterpret_cast<cudaStream_t>(stream), 1, PDL_SMALL,
+                      tmWavHi, tmWavLo, tmDftHi, tmDftLo, tmMelHi, tmMelLo, a));
   return ACX_OK;
 }

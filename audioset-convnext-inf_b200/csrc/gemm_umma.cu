@@ -130,6 +130,8 @@ __global__ void __launch_bounds__(GemmCfg<BN, NEPI, CG>::THREADS, 1)
   if (CG == 2) ptx::cluster_sync_all();            // peer barriers are initialised before any remote arrive / TMA
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();       // TMEM is ours: the next kernel's CTAs may start their prologue on SMs that free up
+  pdl_wait();          // everything above touched only weights; A, the residual and the output belong to earlier kernels
 
   const int num_m_tiles = (g.M + Cfg::BM * CG - 1) / (Cfg::BM * CG);   // tiles of 128 (CG=1) or 256 (CG=2) rows
   const int num_n_tiles = g.N / BN;
@@ -377,19 +379,8 @@ static int launch_umma_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, cons
   ACX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int tiles = ceil_div(g.M, Cfg::BM * CG) * (g.N / BN);      // work units: CTAs (CG=1) or CTA pairs (CG=2)
   const int units = sms / CG;
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((tiles < units ? tiles : units) * CG);
-  cfg.blockDim = dim3(Cfg::THREADS);
-  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CG;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = CG == 2 ? 1 : 0;
-  ACX_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmOut, g));
+  ACX_CUDA(launch_pdl(kern, dim3((tiles < units ? tiles : units) * CG), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, st, CG, PDL_GEMM, tmA, tmB,
+                      tmOut, g));
   return ACX_OK;
 }
 

@@ -278,6 +278,8 @@ __global__ void __launch_bounds__(S* C / 2, dw_min_blocks(S* C / 2))
   // The first PF input rows are requested BEFORE the tap fill so that their L2/HBM latency overlaps the fill's own
   // round trip and barrier (ncu: the serial prologue was ~30 % of a block's lifetime).
   static_assert((R + 6) % PF == 0, "prefetch ring must divide the row count");
+  pdl_trigger();       // programmatic dependent launch (common.cuh); x is the previous kernel's output
+  pdl_wait();
   PT nxt[PF][13];
 #pragma unroll
   for (int k = 0; k < PF; ++k) load_row((int)blockIdx.y * groups_per_block * R - 3 + k, nxt[k]);
@@ -464,6 +466,8 @@ __global__ void __launch_bounds__(256, 3)
   // loads: 3 blocks per SM instead of 2 keep more bytes in flight (ncu: 21 % occupancy, 42-59 % of HBM before)
   const float* gp = ln_w + lig * CH;
   const float* bp = ln_b + lig * CH;
+  pdl_trigger();       // programmatic dependent launch (common.cuh); x is the previous kernel's output
+  pdl_wait();
   float v[NPIX][CH];
   size_t dst_off[NPIX];
   bool ok[NPIX];
@@ -554,6 +558,8 @@ __global__ void __launch_bounds__(256)
   using P = Pair<T>;
   using PT = typename P::type;
   __shared__ float2 smax[8][32], ssum[8][32];
+  pdl_trigger();       // programmatic dependent launch (common.cuh)
+  pdl_wait();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int b = blockIdx.y;
   const int cp = blockIdx.x * 32 + lane;                 // channel pair
@@ -608,6 +614,8 @@ __global__ void __launch_bounds__(256)
   constexpr int MAXC = 4;  // C <= 1024
   extern __shared__ float sv[];  // C floats
   __shared__ float scratch[8];
+  pdl_trigger();       // programmatic dependent launch (common.cuh); `pooled` is head_pool's output
+  pdl_wait();
   const int b = blockIdx.x;
   const int tid = threadIdx.x;
   float val[MAXC], part = 0.f;
@@ -667,6 +675,8 @@ __global__ void __launch_bounds__(256)
 template <typename T>
 __global__ void nhwc_to_nchw_kernel(const T* __restrict__ x, float* __restrict__ out, int HW, int C) {
   __shared__ float tile[32][33];
+  pdl_trigger();       // programmatic dependent launch (common.cuh)
+  pdl_wait();
   const int b = blockIdx.z;
   const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
   const T* xb = x + (size_t)b * HW * C;
@@ -726,9 +736,8 @@ static int launch_dwconv(const void* x, const void* w, const float* bias, const 
   int gpb = (C >= 768 && row_groups >= 4) ? 4 : 1;
   if (gpb_env > 0) gpb = gpb_env < row_groups ? gpb_env : row_groups;
   dim3 grid(strips / S, ceil_div(row_groups, gpb), B);
-  kern<<<grid, S * C / 2, SMEM, st>>>(reinterpret_cast<const T*>(x), reinterpret_cast<const T*>(w), bias, ln_w, ln_b,
-                                      reinterpret_cast<T*>(y), H, W, gpb);
-  ACX_CUDA(cudaGetLastError());
+  ACX_CUDA(launch_pdl(kern, grid, dim3(S * C / 2), SMEM, st, 1, PDL_SMALL, reinterpret_cast<const T*>(x), reinterpret_cast<const T*>(w), bias,
+                      ln_w, ln_b, reinterpret_cast<T*>(y), H, W, gpb));
   return ACX_OK;
 }
 
@@ -867,8 +876,8 @@ int acx_ln_patchify(const void* x, const float* ln_w, const float* ln_b, void* a
   const int blocks = (int)((lanes + 255) / 256);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
 #define ACX_LNP(TT, CC)                                                                                     \
-  ln_patchify_kernel<TT, CC><<<blocks, 256, 0, st>>>(reinterpret_cast<const TT*>(x), ln_w, ln_b,             \
-                                                     reinterpret_cast<TT*>(a), B, H, W)
+  ACX_CUDA(launch_pdl(ln_patchify_kernel<TT, CC>, dim3(blocks), dim3(256), 0, st, 1, PDL_SMALL, reinterpret_cast<const TT*>(x), ln_w, \
+                      ln_b, reinterpret_cast<TT*>(a), B, H, W))
   if (act_dtype == ACX_BF16) {
     if (C == 96) ACX_LNP(bf16, 96); else if (C == 192) ACX_LNP(bf16, 192); else ACX_LNP(bf16, 384);
   } else {
@@ -889,16 +898,9 @@ int acx_ln_patchify_gp(const void* x, const float* ln_w, const float* ln_b, void
   const long long lanes = (total + 1) / 2 * (C / 24);
   const int blocks = (int)((lanes + 255) / 256);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (C == 96)
-    ln_patchify_kernel<bf16, 96, true><<<blocks, 256, 0, st>>>(reinterpret_cast<const bf16*>(x), ln_w, ln_b,
-                                                               reinterpret_cast<bf16*>(a), B, H, W);
-  else if (C == 192)
-    ln_patchify_kernel<bf16, 192, true><<<blocks, 256, 0, st>>>(reinterpret_cast<const bf16*>(x), ln_w, ln_b,
-                                                                reinterpret_cast<bf16*>(a), B, H, W);
-  else
-    ln_patchify_kernel<bf16, 384, true><<<blocks, 256, 0, st>>>(reinterpret_cast<const bf16*>(x), ln_w, ln_b,
-                                                                reinterpret_cast<bf16*>(a), B, H, W);
-  ACX_CUDA(cudaGetLastError());
+  auto kern = C == 96 ? ln_patchify_kernel<bf16, 96, true> : C == 192 ? ln_patchify_kernel<bf16, 192, true> : ln_patchify_kernel<bf16, 384, true>;
+  ACX_CUDA(launch_pdl(kern, dim3(blocks), dim3(256), 0, st, 1, PDL_SMALL, reinterpret_cast<const bf16*>(x), ln_w, ln_b, reinterpret_cast<bf16*>(a), B,
+                      H, W));
   return ACX_OK;
 }
 
@@ -911,14 +913,12 @@ int acx_head(const void* x, const float* ln_w, const float* ln_b, const float* f
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   dim3 pgrid(C / 64, B);
   if (act_dtype == ACX_BF16)
-    head_pool_kernel<bf16><<<pgrid, 256, 0, st>>>(reinterpret_cast<const bf16*>(x), pooled, H, W, C);
+    ACX_CUDA(launch_pdl(head_pool_kernel<bf16>, pgrid, dim3(256), 0, st, 1, PDL_SMALL, reinterpret_cast<const bf16*>(x), pooled, H, W, C));
   else
-    head_pool_kernel<float><<<pgrid, 256, 0, st>>>(reinterpret_cast<const float*>(x), pooled, H, W, C);
-  ACX_CUDA(cudaGetLastError());
+    ACX_CUDA(launch_pdl(head_pool_kernel<float>, pgrid, dim3(256), 0, st, 1, PDL_SMALL, reinterpret_cast<const float*>(x), pooled, H, W, C));
   dim3 fgrid(B, n_cls > 0 ? 8 : 1);
-  head_ln_fc_kernel<<<fgrid, 256, C * sizeof(float), st>>>(pooled, ln_w, ln_b, fc_w, fc_b, scene, logits, probs, C,
-                                                           n_cls);
-  ACX_CUDA(cudaGetLastError());
+  ACX_CUDA(launch_pdl(head_ln_fc_kernel, fgrid, dim3(256), C * sizeof(float), st, 1, PDL_SMALL, pooled, ln_w, ln_b, fc_w, fc_b, scene, logits,
+                      probs, C, n_cls));
   return ACX_OK;
 }
 
@@ -928,10 +928,9 @@ int acx_nhwc_to_nchw_f32(const void* x, float* out, int B, int H, int W, int C, 
   dim3 grid(ceil_div(HW, 32), ceil_div(C, 32), B), block(32, 8);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (act_dtype == ACX_BF16)
-    nhwc_to_nchw_kernel<bf16><<<grid, block, 0, st>>>(reinterpret_cast<const bf16*>(x), out, HW, C);
+    ACX_CUDA(launch_pdl(nhwc_to_nchw_kernel<bf16>, grid, block, 0, st, 1, PDL_SMALL, reinterpret_cast<const bf16*>(x), out, HW, C));
   else
-    nhwc_to_nchw_kernel<float><<<grid, block, 0, st>>>(reinterpret_cast<const float*>(x), out, HW, C);
-  ACX_CUDA(cudaGetLastError());
+    ACX_CUDA(launch_pdl(nhwc_to_nchw_kernel<float>, grid, block, 0, st, 1, PDL_SMALL, reinterpret_cast<const float*>(x), out, HW, C));
   return ACX_OK;
 }
 

@@ -227,6 +227,8 @@ __global__ void __launch_bounds__(512, 1)
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int num_tiles = (a.M + Cfg::BM - 1) / Cfg::BM;
+  pdl_trigger();                  // TMEM is allocated: dependents may start their prologue where SMs free up
+  if (warp != 0) pdl_wait();      // the weight-stream producer touches only weights and may run ahead of the previous kernel
 
   if (warp == 3) {
     // ===================== y-tile producer ==================================================================
@@ -669,6 +671,8 @@ __global__ void __launch_bounds__(512, 1)
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int num_tiles = (a.M + Cfg::BM - 1) / Cfg::BM;
+  pdl_trigger();                  // TMEM is allocated: dependents may start their prologue where SMs free up
+  if (warp != 0) pdl_wait();      // warp 0 first requests the resident weights (144 KB, independent of the previous kernel)
 
   if (warp == 0) {
     // ===================== producer: weights once, then one y tile per row tile ==============================
@@ -679,6 +683,7 @@ __global__ void __launch_bounds__(512, 1)
         ptx::tma_load_2d(smem + Cfg::OFF_W1T + h * 8192, &tmW1t, w_full, 64, h * 128);
       }
       for (int kb = 0; kb < 6; ++kb) ptx::tma_load_2d(smem + Cfg::OFF_W2 + kb * 12288, &tmW2, w_full, kb * 64, 0);
+      pdl_wait();                 // the y tiles are the previous kernel's output
       int it = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
         ptx::mbar_wait(a_empty, (it & 1) ^ 1);
@@ -1058,10 +1063,8 @@ static int launch_mlp96_resident(const void* y, void* x, const void* w1, const f
   a.trace = nullptr;
 #endif
   const int grid = tiles < sms ? tiles : sms;
-  if (gp && ln_s) mlp_fused96_kernel<true, true><<<grid, 512, Cfg::SMEM_BYTES, st>>>(tmYm, tmYt, tmW1m, tmW1t, tmW2, tmOut, a);
-  else if (gp) mlp_fused96_kernel<true, false><<<grid, 512, Cfg::SMEM_BYTES, st>>>(tmYm, tmYt, tmW1m, tmW1t, tmW2, tmOut, a);
-  else mlp_fused96_kernel<false, false><<<grid, 512, Cfg::SMEM_BYTES, st>>>(tmYm, tmYt, tmW1m, tmW1t, tmW2, tmOut, a);
-  ACX_CUDA(cudaGetLastError());
+  auto kern = gp && ln_s ? mlp_fused96_kernel<true, true> : gp ? mlp_fused96_kernel<true, false> : mlp_fused96_kernel<false, false>;
+  ACX_CUDA(launch_pdl(kern, dim3(grid), dim3(512), Cfg::SMEM_BYTES, st, 1, PDL_MLP, tmYm, tmYt, tmW1m, tmW1t, tmW2, tmOut, a));
   return ACX_OK;
 }
 
@@ -1100,10 +1103,8 @@ static int launch_mlp(const void* y, void* x, const void* w1, const float* b1, c
   a.ln_s = ln_s;
   a.trace = nullptr;
   const int grid = tiles < sms ? tiles : sms;
-  if (gp && ln_s) mlp_fused_kernel<C, true, true><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(tmY, tmW1, tmW2, tmOut, a);
-  else if (gp) mlp_fused_kernel<C, true, false><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(tmY, tmW1, tmW2, tmOut, a);
-  else mlp_fused_kernel<C, false, false><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(tmY, tmW1, tmW2, tmOut, a);
-  ACX_CUDA(cudaGetLastError());
+  auto kern = gp && ln_s ? mlp_fused_kernel<C, true, true> : gp ? mlp_fused_kernel<C, true, false> : mlp_fused_kernel<C, false, false>;
+  ACX_CUDA(launch_pdl(kern, dim3(grid), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, st, 1, PDL_MLP, tmY, tmW1, tmW2, tmOut, a));
   return ACX_OK;
 }
 

@@ -84,6 +84,8 @@ __global__ void __launch_bounds__(128, 4)
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_d = *tmem_slot;
+  pdl_trigger();       // programmatic dependent launch (common.cuh): weights split, TMEM allocated
+  pdl_wait();          // the log-mel is the front end's output
   const uint32_t lane_taddr = tmem_d + (static_cast<uint32_t>(warp * 32) << 16);
   const uint32_t sbase = ptx::smem_u32(smem);
   const uint64_t dAhi = ptx::umma_desc_sw128_kmajor(sbase + Cfg::OFF_AHI);
@@ -220,9 +222,8 @@ int launch_stem_umma(const float* logmel, const float* w, const float* bias, con
   const long long tiles = (total + Cfg::BM - 1) / Cfg::BM;
   const long long want = 4LL * sms;                              // 4 resident CTAs per SM (4 x 128 TMEM columns)
   const int grid = (int)(tiles < want ? tiles : want);
-  stem_umma_kernel<<<grid, 128, Cfg::SMEM_BYTES, st>>>(logmel, w, bias, ln_w, ln_b, reinterpret_cast<bf16*>(out), T,
-                                                       n_mels, H0, W0, total, gp);
-  ACX_CUDA(cudaGetLastError());
+  ACX_CUDA(launch_pdl(stem_umma_kernel, dim3(grid), dim3(128), Cfg::SMEM_BYTES, st, 1, PDL_SMALL, logmel, w, bias, ln_w, ln_b,
+                      reinterpret_cast<bf16*>(out), T, n_mels, H0, W0, total, gp));
   return ACX_OK;
 }
 

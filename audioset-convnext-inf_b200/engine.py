@@ -99,6 +99,8 @@ class PackedWeights:
                 ln_b=g(f"downsample_layers.{i}.0.bias").contiguous(),
                 w=w.permute(0, 2, 3, 1).reshape(cout, 4 * cin).to(adt).contiguous(),   # k = (dy, dx, cin)
                 b=g(f"downsample_layers.{i}.1.bias").contiguous()))
+            if precision == "bf16":
+                self.ds[-1]["w_fused"] = pack_downsample_weight(w).to(adt).contiguous()
 
         # ---- blocks -------------------------------------------------------------------------
         self.blocks = []
@@ -133,6 +135,14 @@ def fold_layernorm_into_pwconv1(w1, b1, ln_w, ln_b):
     w1f = (w1.double() * ln_w.double()[None, :]).to(torch.float32).to(torch.bfloat16).contiguous()
     return dict(w1f=w1f, s1=w1f.double().sum(1).to(torch.float32).contiguous(),
                 b1f=(b1.double() + w1.double() @ ln_b.double()).to(torch.float32).contiguous())
+
+
+def pack_downsample_weight(w):
+    """Conv2d(k2, s2) weight (Cout, Cin, 2, 2) -> (Cout, 4 Cin) with k = ((dy * Cin/8 + g) * 2 + dx) * 8 + c8: the K order of
+    acx_downsample_fused_gp, in which the two horizontally adjacent pixels of a patch are 32 contiguous bytes of a
+    group-planar plane and of the operand row (CX:231-234)."""
+    cout, cin = w.shape[0], w.shape[1]
+    return w.reshape(cout, cin // 8, 8, 2, 2).permute(0, 3, 1, 4, 2).reshape(cout, 4 * cin)
 
 
 def _split_f16(x):
@@ -183,6 +193,8 @@ class Engine:
         # where the Block's LayerNorm runs behind the tensor-core conv: "fused" = on the operand tile inside the fused
         # MLP kernel (stages 0-1), "pass" = acx_layernorm_rows over HBM (always for stages whose MLP is two GEMMs)
         self.ln_mode = os.environ.get("ACX_LN", "fused")
+        # downsample layers behind a planar stage: "1" = one implicit-GEMM kernel (ds_fused.cu), "0" = ln_patchify + GEMM
+        self.ds_fused = os.environ.get("ACX_DS_FUSED", "1") == "1"
         if precision == "fp32":
             self.frontend, self.mlp, self.dwconv = "simt", "gemm", "simt"
         # LRU of workspaces keyed by (clips, samples); each owns the CUDA graphs captured over its buffers, so a
@@ -270,6 +282,10 @@ class Engine:
         tensor counted once per producing / consuming kernel, split-precision passes counted once."""
         T, hs = out_time_dims(L)
         es = self.esize
+        if tag.startswith("ds_fused_c"):      # x read once, the stage's input written once; the patch matrix never exists
+            C = int(tag[len("ds_fused_c"):])
+            s = DIMS.index(C)
+            return "hbm", 1.0 * n * es * (hs[s] * (56 >> s) * C + hs[s + 1] * (28 >> s) * 2 * C)
         if tag.startswith(("pw1_gelu", "pw2_resid", "ds_")):
             K, Nn = (int(t[1:]) for t in tag.split("_")[-2:])
             C = {"pw1_gelu": K, "pw2_resid": Nn, "ds": K // 4}[tag.rsplit("_", 2)[0]]
@@ -344,11 +360,12 @@ class Engine:
     def _trunk(self, ws, n, st):
         w = self.w
         x, y, hid = ws["x"].data_ptr(), ws["y"].data_ptr(), ws["hid"].data_ptr()
+        xgp = ws["xg"].data_ptr() if "xg" in ws else 0      # planar residual stream; trades places with y at a fused downsample
         fused0 = self.mlp == "fused" and self.dwconv == "tc" and 0 in self.dwconv_tc_stages and self.gp
         stem_gp = fused0 and os.environ.get("ACX_STEM", "") != "simt"     # the stem writes stage 0's planar layout itself
         if stem_gp:
             self._call("stem", "acx_stem_gp", ws["logmel"].data_ptr(), w.stem_w.data_ptr(), w.stem_b.data_ptr(),
-                       w.stem_ln_w.data_ptr(), w.stem_ln_b.data_ptr(), ws["xg"].data_ptr(), n, ws["T"], N_MELS, st)
+                       w.stem_ln_w.data_ptr(), w.stem_ln_b.data_ptr(), xgp, n, ws["T"], N_MELS, st)
         else:
             self._call("stem", "acx_stem", ws["logmel"].data_ptr(), w.stem_w.data_ptr(), w.stem_b.data_ptr(),
                        w.stem_ln_w.data_ptr(), w.stem_ln_b.data_ptr(), x, n, ws["T"], N_MELS, self.adt, st)
@@ -362,7 +379,7 @@ class Engine:
             gp = tc and fused_mlp and self.gp and Wd in (56, 28)
             gp2 = tc and not fused_mlp and self.gp and self.mlp == "fused" and Wd == 14 and C == 384   # planar, two-GEMM MLP
             if gp2:
-                xg, vg = ws["xg"].data_ptr(), y
+                xg, vg = xgp, y
                 if not entered_gp:
                     self._call(f"to_gp_c{C}", "acx_gp_transpose", x, xg, M, C, 1, st)
                 stats = ws["stats"].data_ptr()
@@ -375,7 +392,7 @@ class Engine:
                                blk["b2"].data_ptr(), blk["gamma"].data_ptr(), st)
             elif gp:
                 # group-planar residual stream for this stage: xg <- x; the row-major x buffer becomes the conv output
-                xg, vg = ws["xg"].data_ptr(), x
+                xg, vg = xgp, x
                 if not (s == 0 and stem_gp) and not entered_gp:
                     self._call(f"to_gp_c{C}", "acx_gp_transpose", x, xg, M, C, 1, st)
             for blk in (() if gp2 else w.blocks[s]):
@@ -414,18 +431,26 @@ class Engine:
                                blk["b2"].data_ptr(), blk["gamma"].data_ptr(), x, st)
             if s < 3:
                 d = w.ds[s]
+                # the next stage takes its input group-planar: the downsample GEMM writes that layout itself
+                entered_gp = (self.precision == "bf16" and self.mlp == "fused" and 2 * C in (96, 192, 384) and self.dwconv == "tc"
+                              and (s + 1) in self.dwconv_tc_stages and self.gp and Wd // 2 in (56, 28, 14)
+                              and os.environ.get("ACX_DS_GP", "1") == "1")
+                if (gp or gp2) and self.ds_fused:
+                    # LayerNorm + 2x2 patch gather + GEMM in one kernel: the patch matrix never reaches HBM (ds_fused.cu)
+                    self._call(f"ds_fused_c{C}", "acx_downsample_fused_gp", xg, d["ln_w"].data_ptr(), d["ln_b"].data_ptr(),
+                               d["w_fused"].data_ptr(), d["b"].data_ptr(), y if entered_gp else x, n, H, Wd, C, 1 if entered_gp else 0, st)
+                    if entered_gp:
+                        xgp, y = y, xgp      # the kernel cannot write the planes it is still reading: the buffers trade places
+                    Wd //= 2
+                    continue
                 if gp or gp2:
                     self._call(f"ln_patchify_c{C}", "acx_ln_patchify_gp", xg, d["ln_w"].data_ptr(), d["ln_b"].data_ptr(), y, n, H, Wd, C, st)
                 else:
                     self._call(f"ln_patchify_c{C}", "acx_ln_patchify", x, d["ln_w"].data_ptr(), d["ln_b"].data_ptr(), y, n, H, Wd, C, self.adt, st)
                 Wd //= 2
                 Mo = n * ws["hs"][s + 1] * Wd
-                # the next stage takes its input group-planar: the downsample GEMM writes that layout itself
-                entered_gp = (self.precision == "bf16" and self.mlp == "fused" and 2 * C in (96, 192, 384) and self.dwconv == "tc"
-                              and (s + 1) in self.dwconv_tc_stages and self.gp and Wd in (56, 28, 14)
-                              and os.environ.get("ACX_DS_GP", "1") == "1")
                 if entered_gp:
-                    self._call(f"ds_k{4 * C}_n{2 * C}", "acx_gemm_bf16_gp_out", y, d["w"].data_ptr(), ws["xg"].data_ptr(), Mo, 2 * C, 4 * C,
+                    self._call(f"ds_k{4 * C}_n{2 * C}", "acx_gemm_bf16_gp_out", y, d["w"].data_ptr(), xgp, Mo, 2 * C, 4 * C,
                                d["b"].data_ptr(), st)
                 else:
                     self._gemm(y, d["w"].data_ptr(), x, Mo, 2 * C, 4 * C, N.EPI_BIAS, d["b"].data_ptr(), 0, 0, st)

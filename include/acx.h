@@ -126,6 +126,14 @@ ACX_API int acx_ln_patchify(const void* x, const float* ln_w, const float* ln_b,
 ACX_API int acx_ln_patchify_gp(const void* x, const float* ln_w, const float* ln_b, void* a, int B, int H, int W, int C,
                        void* stream);
 
+/* ---- the whole downsample layer as one implicit GEMM (CX:230-235: LayerNorm(channels_first) -> Conv2d(k2, s2)) ----
+ * x group-planar bf16 [C/8][Mp][8] (Mp = B*H*W rounded up to 128); the LayerNorm'd 2x2 patches are formed in shared memory
+ * as the tensor-core A operand (no patch matrix in HBM).  w: (2C, 4C) bf16, k = ((dy * C/8 + g) * 2 + dx) * 8 + c8 for
+ * input channel 8 g + c8 at patch position (dy, dx).  out: (B*(H/2)*(W/2), 2C) bf16 row-major, or group-planar
+ * [2C/8][Mp_out][8] when out_gp.  C = 96 / 192 / 384, W even (an odd last row of H is dropped like the conv does). */
+ACX_API int acx_downsample_fused_gp(const void* x, const float* ln_w, const float* ln_b, const void* w, const float* bias,
+                            void* out, int B, int H, int W, int C, int out_gp, void* stream);
+
 /* ---- GEMMs: out[M,N] = epi(A[M,K] . W[N,K]^T)  (nn.Linear / conv-as-GEMM weight layout) ------ */
 /* bf16 operands, fp32 accumulation in TMEM (tcgen05.mma, TMA-fed).  K % 8 == 0, N % 32 == 0. */
 ACX_API int acx_gemm_bf16(const void* A, const void* W, void* out, int M, int N, int K, int epilogue,

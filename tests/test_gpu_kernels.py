@@ -250,6 +250,54 @@ def test_ln_patchify_then_gemm_is_downsample(sd, stage, H, dtype):
     assert (out - ref).abs().max() < (1e-3 if dtype == torch.float32 else 6e-2)
 
 
+@pytest.mark.parametrize("out_gp", [0, 1])
+@pytest.mark.parametrize("stage,H,B", [(0, 10, 2), (0, 252, 3), (0, 7, 1), (1, 126, 2), (1, 9, 3), (2, 63, 3), (2, 6, 1), (2, 64, 5)])
+def test_downsample_fused_implicit_gemm(sd, stage, H, B, out_gp):
+    """acx_downsample_fused_gp (LayerNorm + 2x2/s2 patch gather + GEMM in one kernel, CX:230-235) against the oracle's
+    downsample layer on the same bf16 input, and against the two-kernel form (acx_ln_patchify_gp + acx_gemm_bf16) it
+    replaces; odd H (last row dropped), row counts that are not multiples of the 128-row tile, both output layouts."""
+    from audioset_convnext_inf_b200.engine import pack_downsample_weight
+    C, Wd = O.DIMS[stage], 56 >> stage
+    i = stage + 1
+    g = torch.Generator().manual_seed(100 * stage + H)
+    xq = (torch.randn(B, H, Wd, C, generator=g) * 1.3 + 0.2).to(torch.bfloat16)
+    ref = O.downsample(xq.float().permute(0, 3, 1, 2), sd, i, torch.float32).permute(0, 2, 3, 1)   # (B, Ho, Wo, 2C)
+    Ho, Wo = H // 2, Wd // 2
+    M, Mo = B * H * Wd, B * Ho * Wo
+    Mp, Mop = (M + 127) // 128 * 128, (Mo + 127) // 128 * 128
+    xg = torch.zeros(C // 8, Mp, 8, device=DEV, dtype=torch.bfloat16)
+    xg[:, :M] = xq.to(DEV).view(M, C // 8, 8).permute(1, 0, 2)
+    lw, lb = sd[f"downsample_layers.{i}.0.weight"].to(DEV), sd[f"downsample_layers.{i}.0.bias"].to(DEV)
+    w4 = sd[f"downsample_layers.{i}.1.weight"]
+    bias = sd[f"downsample_layers.{i}.1.bias"].to(DEV)
+    wf = pack_downsample_weight(w4).to(torch.bfloat16).contiguous().to(DEV)
+    if out_gp:
+        outg = torch.full((2 * C // 8, Mop, 8), float("nan"), device=DEV, dtype=torch.bfloat16)
+        N.call("acx_downsample_fused_gp", xg.data_ptr(), lw.data_ptr(), lb.data_ptr(), wf.data_ptr(), bias.data_ptr(),
+               outg.data_ptr(), B, H, Wd, C, 1, _st())
+        out = outg[:, :Mo].permute(1, 0, 2).reshape(Mo, 2 * C)
+    else:
+        out = torch.full((Mo + 3, 2 * C), float("nan"), device=DEV, dtype=torch.bfloat16)
+        N.call("acx_downsample_fused_gp", xg.data_ptr(), lw.data_ptr(), lb.data_ptr(), wf.data_ptr(), bias.data_ptr(),
+               out.data_ptr(), B, H, Wd, C, 0, _st())
+        torch.cuda.synchronize()
+        assert torch.isnan(out[Mo:].float()).all(), "wrote past the last output row"
+        out = out[:Mo]
+    # the two-kernel form on the same input
+    a = torch.empty(Mo, 4 * C, device=DEV, dtype=torch.bfloat16)
+    N.call("acx_ln_patchify_gp", xg.data_ptr(), lw.data_ptr(), lb.data_ptr(), a.data_ptr(), B, H, Wd, C, _st())
+    wk = w4.permute(0, 2, 3, 1).reshape(2 * C, 4 * C).to(torch.bfloat16).contiguous().to(DEV)
+    out2 = torch.empty(Mo, 2 * C, device=DEV, dtype=torch.bfloat16)
+    N.call("acx_gemm_bf16", a.data_ptr(), wk.data_ptr(), out2.data_ptr(), Mo, 2 * C, 4 * C, N.EPI_BIAS, bias.data_ptr(), 0, 0, _st())
+    torch.cuda.synchronize()
+    of = out.float().cpu()
+    assert torch.isfinite(of).all(), "unwritten outputs"
+    err = (of - ref.reshape(Mo, 2 * C)).abs().max().item()
+    assert err < 6e-2, err                                    # the bound test_ln_patchify_then_gemm_is_downsample uses (bf16)
+    d2 = (of - out2.float().cpu()).abs()
+    assert d2.max().item() < 3.2e-2 and d2.mean().item() < 1e-3, (d2.max().item(), d2.mean().item())
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("H", [31, 9])
 def test_head_and_frame_layout(sd, H, dtype):
