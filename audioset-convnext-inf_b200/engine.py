@@ -194,7 +194,10 @@ class Engine:
         # MLP kernel (stages 0-1), "pass" = acx_layernorm_rows over HBM (always for stages whose MLP is two GEMMs)
         self.ln_mode = os.environ.get("ACX_LN", "fused")
         # downsample layers behind a planar stage: "1" = one implicit-GEMM kernel (ds_fused.cu), "0" = ln_patchify + GEMM
+        # which input widths take it: at C = 384 (109 row tiles, N = 768 in two halves that both repeat the gather) the
+        # two-kernel form measured faster (66 vs 74 us per 64 clips), so the default is the two large layers
         self.ds_fused = os.environ.get("ACX_DS_FUSED", "1") == "1"
+        self.ds_fused_widths = tuple(int(c) for c in os.environ.get("ACX_DS_FUSED_C", "96,192").split(",") if c)
         if precision == "fp32":
             self.frontend, self.mlp, self.dwconv = "simt", "gemm", "simt"
         # LRU of workspaces keyed by (clips, samples); each owns the CUDA graphs captured over its buffers, so a
@@ -435,7 +438,7 @@ class Engine:
                 entered_gp = (self.precision == "bf16" and self.mlp == "fused" and 2 * C in (96, 192, 384) and self.dwconv == "tc"
                               and (s + 1) in self.dwconv_tc_stages and self.gp and Wd // 2 in (56, 28, 14)
                               and os.environ.get("ACX_DS_GP", "1") == "1")
-                if (gp or gp2) and self.ds_fused:
+                if (gp or gp2) and self.ds_fused and C in self.ds_fused_widths:
                     # LayerNorm + 2x2 patch gather + GEMM in one kernel: the patch matrix never reaches HBM (ds_fused.cu)
                     self._call(f"ds_fused_c{C}", "acx_downsample_fused_gp", xg, d["ln_w"].data_ptr(), d["ln_b"].data_ptr(),
                                d["w_fused"].data_ptr(), d["b"].data_ptr(), y if entered_gp else x, n, H, Wd, C, 1 if entered_gp else 0, st)

@@ -396,11 +396,13 @@ def test_amplitude_contract_check_is_opt_in(models, monkeypatch):
 
 
 @pytest.mark.parametrize("env", [{"ACX_DWCONV": "simt"}, {"ACX_GP": "0"}, {"ACX_LN": "smem"}, {"ACX_DWCONV_TC_STAGES": "0"},
-                                 {"ACX_DS_GP": "0"}])
+                                 {"ACX_DS_GP": "0"}, {"ACX_DS_FUSED": "0"}, {"ACX_DS_FUSED_C": "96,192,384"}, {"ACX_PDL": "0"},
+                                 {"ACX_PDL": "31"}])
 def test_alternative_kernel_routes_agree(parity_sd, monkeypatch, env):
     """Every selectable route of the block -- CUDA-core depthwise conv + fused LayerNorm (round 1), tensor-core conv on
     row-major tensors, LayerNorm applied in shared memory instead of folded, planar layout in stage 0 only, transpose pass
-    instead of a planar downsample GEMM -- gives the same logits as the default route within the bf16-mode tolerance:
+    instead of a planar downsample GEMM, ln_patchify + GEMM instead of the implicit-GEMM downsample kernel (and that kernel at
+    all three widths), programmatic dependent launch off / on for every kernel family -- gives the same logits as the default route within the bf16-mode tolerance:
     the routes differ only in where roundings to bf16 happen."""
     wave = weights.make_waveforms(2, n_samples=64000, kind="tones", seed=3).to(DEV)
 
