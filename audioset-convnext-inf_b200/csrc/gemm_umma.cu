@@ -28,6 +28,9 @@ struct GemmArgs {
   int a_gp;     // 1: A is group-planar [K/8][Mp][8]: operand tiles arrive as 3-D boxes in the un-swizzled K-major layout
   const float2* stats;   // EPI_BIAS_GELU_FOLD: per-row (rstd, -mean * rstd) of A (acx_gp_row_stats)
   const float* ln_s;     // EPI_BIAS_GELU_FOLD: s[j] = sum_k W[j, k] of the LayerNorm-folded weights
+  int reverse;           // walk the tiles from the last row block to the first: a consumer of a tensor LARGER than L2 that the
+                         // previous kernel wrote front to back (pwconv2 reading the 173 MB hidden tensor of stage 2) then
+                         // starts with the part that is still in L2 instead of evicting it on the way there
 };
 constexpr int ACX_EPI_BIAS_GELU_FOLD = 3;   // internal: GELU epilogue with the LayerNorm applied as a rank-1 correction
 
@@ -144,8 +147,9 @@ __global__ void __launch_bounds__(GemmCfg<BN, NEPI, CG>::THREADS, 1)
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = unit; tile < num_tiles; tile += num_units) {
-        const int m0 = (tile / num_n_tiles) * Cfg::BM * CG + cta_rank * Cfg::BM;
-        const int n0 = (tile % num_n_tiles) * BN + cta_rank * (BN / CG);
+        const int tt = g.reverse ? num_tiles - 1 - tile : tile;      // see GemmArgs::reverse
+        const int m0 = (tt / num_n_tiles) * Cfg::BM * CG + cta_rank * Cfg::BM;
+        const int n0 = (tt % num_n_tiles) * BN + cta_rank * (BN / CG);
         for (int kb = 0; kb < num_kb; ++kb) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
@@ -230,8 +234,9 @@ __global__ void __launch_bounds__(GemmCfg<BN, NEPI, CG>::THREADS, 1)
     for (int tile = unit; tile < num_tiles; tile += num_units, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      const int m0 = (tile / num_n_tiles) * Cfg::BM * CG + cta_rank * Cfg::BM;
-      const int n0 = (tile % num_n_tiles) * BN;
+      const int tt = g.reverse ? num_tiles - 1 - tile : tile;
+      const int m0 = (tt / num_n_tiles) * Cfg::BM * CG + cta_rank * Cfg::BM;
+      const int n0 = (tt % num_n_tiles) * BN;
       const int row0 = m0 + quad * 32;
       uint4 rq[4];
       auto fetch_resid = [&](int ci) {
@@ -459,6 +464,9 @@ static int gemm_bf16_impl(const void* A, const void* W, void* out, int M, int N,
   g.a_gp = a_gp;
   g.stats = reinterpret_cast<const float2*>(stats);
   g.ln_s = ln_s;
+  static const bool rev_ok = getenv("ACX_GEMM_REVERSE") == nullptr || atoi(getenv("ACX_GEMM_REVERSE")) != 0;
+  // the pwconv2 GEMMs (residual epilogue) consume what pwconv1 has just written front to back
+  g.reverse = rev_ok && epilogue == ACX_EPI_BIAS_SCALE_RESID && (size_t)M * K * 2 > (size_t)96 << 20;
   CUtensorMap tmA;
   int rc = a_gp ? make_tmap_gp_bf16(&tmA, A, (uint64_t)M, (uint64_t)K / 8, 128, 8)
                 : make_tmap_2d_bf16(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)K * 2, 64, 128);
