@@ -24,6 +24,9 @@ SIGNATURES = {
     "acx_wave_prep_pcm16": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     "acx_power_mel_log": [_vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp],
     "acx_frontend_fused": [_vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
+    "acx_frame_fold": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
+    "acx_frame_fold_pcm16": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
+    "acx_frontend_folded": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "acx_stem": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "acx_stem_gp": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp],
     "acx_dwconv_ln": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],

@@ -80,6 +80,20 @@ ACX_API int acx_power_mel_log(const float* spec, int ld_spec, int n_bins, const 
  * chunk c rows [0,64) = real rows of bins [64c, 64c+64), rows [64,128) = imag rows.
  * mel_hi/lo: (n_chunks*256, 64) bf16, chunk c rows m<224 = melW[64c + k, m] (K-major), rest 0.
  * out (B, T, n_mels) fp32. */
+/* The same front end on FOLDED frames (frontend_folded.cu): for STFT rows with the real-input symmetry of a periodic-Hann
+ * windowed DFT (W_re even, W_im odd about n = n_fft/2, zero at n = 0; torchlibrosa Spectrogram, CX:179-187) a frame's
+ * spectrum is  re = E . Wre'^T, im = O . Wim'^T  with E[0] = x[512], E[j] = x[j] + x[1024-j], O[0] = 0, O[j] = x[j] - x[1024-j]:
+ * half the tensor-core work of the dense product.
+ *   acx_frame_fold(_pcm16): waveform (B, L) fp32 / int16 PCM -> f_hi / f_lo (B, T, n_fft) fp16 pairs of the
+ *     2^ACX_FE_SCALE_LOG2-scaled folded frames [E (n_fft/2) | O (n_fft/2)], reflect padding (center=True), T = L/hop + 1.
+ *   acx_frontend_folded: w_hi / w_lo (ceil(n_chunks/2)*256, n_fft/2) fp16 pairs, per pair of 64-bin chunks the rows
+ *     [re chunk 2p | re chunk 2p+1 | im chunk 2p | im chunk 2p+1] (engine.fold_dft_weights); mel_* / bn_* / out as below. */
+ACX_API int acx_frame_fold(const float* wave, void* f_hi, void* f_lo, int B, int L, int T, int n_fft, int hop, void* stream);
+ACX_API int acx_frame_fold_pcm16(const int16_t* pcm, void* f_hi, void* f_lo, int B, int L, int T, int n_fft, int hop, void* stream);
+ACX_API int acx_frontend_folded(const void* f_hi, const void* f_lo, const void* w_hi, const void* w_lo, const void* mel_hi,
+                        const void* mel_lo, int n_chunks, const float* bn_scale, const float* bn_shift, float* out,
+                        int B, int T, int n_fft, int n_mels, void* stream);
+
 ACX_API int acx_frontend_fused(const void* hi, const void* lo, int ld_pad, const void* dft_hi, const void* dft_lo,
                        const void* mel_hi, const void* mel_lo, int n_chunks, const float* bn_scale,
                        const float* bn_shift, float* out, int B, int T, int n_fft, int hop, int n_mels,

@@ -340,15 +340,73 @@ def test_frontend_fp32_path_logmel(sd):
         assert err64 < max(3 * ref_err64, 1e-4)
 
 
-@pytest.mark.parametrize("kind,L", [("noise", 64000), ("tones", 64000), ("tones", 320000)])
-def test_frontend_fused_logmel(sd, kind, L):
-    """tcgen05 front end (split-bf16 x3 DFT and mel GEMMs) vs the oracle's torchlibrosa restatement.
+@pytest.mark.parametrize("L", [64000, 40123, 700])
+@pytest.mark.parametrize("pcm", [False, True])
+def test_frame_fold_matches_reflect_padded_frames(L, pcm):
+    """acx_frame_fold: F[b, t, :512] = E, F[b, t, 512:] = O of the reflect-padded frame t (center=True, hop 320), folded in
+    fp32 and carried as a 2^8-scaled fp16 pair: hi + lo reproduces the fp32 fold to the pair's 22 bits."""
+    B, T = 2, L // 320 + 1
+    w = weights.make_waveforms(B, n_samples=L, kind="tones", seed=9)
+    if pcm:
+        wi = (w * 20000).round().clamp(-32768, 32767).to(torch.int16)
+        w = wi.float() / 32767.0                                              # utils/utilities.py:226 (true division)
+    xp = F.pad(w[:, None], (512, 512), mode="reflect")[:, 0]
+    fr = xp.unfold(1, 1024, 320)[:, :T]                                        # (B, T, 1024)
+    mir = torch.arange(1023, 512, -1)
+    E = torch.cat([fr[..., 512:513], fr[..., 1:512] + fr[..., mir]], -1)
+    Od = torch.cat([torch.zeros_like(fr[..., :1]), fr[..., 1:512] - fr[..., mir]], -1)
+    ref = torch.cat([E, Od], -1)
+    hi = torch.full((B, T, 1024), float("nan"), device=DEV, dtype=torch.float16)
+    lo = torch.full_like(hi, float("nan"))
+    src = (wi if pcm else w).to(DEV)
+    N.call("acx_frame_fold_pcm16" if pcm else "acx_frame_fold", src.data_ptr(), hi.data_ptr(), lo.data_ptr(), B, L, T, 1024, 320, _st())
+    got = ((hi.float() + lo.float()) / 256.0).cpu()
+    assert torch.isfinite(got).all()
+    assert (got - ref).abs().max().item() < 2.0 ** -20 * max(1.0, ref.abs().max().item())
+
+
+def test_dft_fold_needs_symmetric_rows(sd):
+    """engine.fold_dft_weights: the periodic-Hann STFT rows of the checkpoint fold (and reproduce the dense product); rows
+    without the real-input symmetry are refused, and the engine then keeps the dense kernel."""
+    import audioset_convnext_inf_b200 as acx
+    from audioset_convnext_inf_b200.engine import fold_dft_weights
+    cr = sd["spectrogram_extractor.stft.conv_real.weight"][:, 0, :].float()
+    ci = sd["spectrogram_extractor.stft.conv_imag.weight"][:, 0, :].float()
+    f = fold_dft_weights(cr, ci, 7)
+    assert f is not None and f.shape == (4 * 256, 512)
+    x = torch.randn(3, 1024, dtype=torch.float64)
+    mir = torch.arange(1023, 512, -1)
+    E = torch.cat([x[:, 512:513], x[:, 1:512] + x[:, mir]], 1)
+    Od = torch.cat([torch.zeros(3, 1, dtype=torch.float64), x[:, 1:512] - x[:, mir]], 1)
+    fr = f.double().view(4, 4, 64, 512)
+    for c in range(7):
+        assert (E @ fr[c // 2, c % 2].t() - x @ cr.double()[64 * c:64 * c + 64].t()).abs().max() < 1e-4
+        assert (Od @ fr[c // 2, 2 + c % 2].t() - x @ ci.double()[64 * c:64 * c + 64].t()).abs().max() < 1e-4
+    bad = cr.clone()
+    bad[5, 100] += 1e-3
+    assert fold_dft_weights(bad, ci, 7) is None
+    sd2 = dict(sd)
+    sd2["spectrogram_extractor.stft.conv_real.weight"] = bad[:, None, :].clone()
+    m = acx.convnext_tiny(drop_path_rate=0.0, after_stem_dim=[252, 56])
+    m.load_state_dict(sd2)
+    m = m.to(DEV).eval().set_precision("bf16")
+    assert m._get_engine().frontend == "fused"
+    w = weights.make_waveforms(1, n_samples=32000, kind="noise", seed=1)
+    assert (m.forward_logmel(w.to(DEV)).cpu() - O.frontend(w, sd2, torch.float32)).abs().max() < 1e-3
+
+
+@pytest.mark.parametrize("frontend", ["folded", "fused"])
+@pytest.mark.parametrize("kind,L", [("noise", 64000), ("tones", 64000), ("tones", 320000), ("tones", 40123)])
+def test_frontend_fused_logmel(sd, kind, L, frontend, monkeypatch):
+    """tcgen05 front end (split-fp16 x3 DFT -- on folded frames by default, dense with ACX_FRONTEND=fused -- and split-bf16
+    x3 mel GEMM) vs the oracle's torchlibrosa restatement.
     Metrics per SURVEY.md Appendix C; values are in bn0-normalised units (1 unit ~ 20 dB here)."""
     import audioset_convnext_inf_b200 as acx
+    monkeypatch.setenv("ACX_FRONTEND", frontend)
     m = acx.convnext_tiny(drop_path_rate=0.0, after_stem_dim=[252, 56])
     m.load_state_dict(sd)
     m = m.to(DEV).eval().set_precision("bf16")
-    assert m._get_engine().frontend == "fused"
+    assert m._get_engine().frontend == frontend
     w = weights.make_waveforms(2, n_samples=L, kind=kind, seed=4)
     ref = O.frontend(w, sd, torch.float32)
     ref64 = O.frontend(w, sd, torch.float64)
@@ -359,7 +417,7 @@ def test_frontend_fused_logmel(sd, kind, L):
     # bins within 80 dB of the clip maximum (un-normalised dB = before bn0)
     raw = O.logmel(O.spectrogram(w, sd, torch.float64), sd, torch.float64)
     mask = raw > raw.amax(dim=(1, 2), keepdim=True) - 80.0
-    print(f"[fused {kind} L={L}] vs fp64: max {err.max():.3e} mean {err.mean():.3e} p99 {err.flatten().quantile(0.99):.3e} "
+    print(f"[{frontend} {kind} L={L}] vs fp64: max {err.max():.3e} mean {err.mean():.3e} p99 {err.flatten().quantile(0.99):.3e} "
           f"masked-max {err[mask].max():.3e} | reference fp32 vs fp64: max {ref_err.max():.3e} mean {ref_err.mean():.3e}")
     assert torch.isfinite(got).all()
     # scaled fp16 pairs keep 22 operand bits: the front end sits within ~2x of the reference's OWN fp32 rounding noise
@@ -383,6 +441,8 @@ def test_c_abi_rejects_bad_arguments_with_messages():
     assert lib.acx_wave_prep(p, p, p, 1, 2000, 1024, 2000, N.ACX_BF16, 0) != 0 and "ld_pad" in N.last_error()
     assert lib.acx_frontend_fused(p, p, 4096, p, p, p, p, 7, p, p, p, 1, 1001, 512, 320, 224, 0) != 0
     assert "n_fft=1024" in N.last_error()
+    assert lib.acx_frontend_folded(p, p, p, p, p, p, 7, p, p, p, 1, 1001, 512, 224, 0) != 0 and "n_fft=1024" in N.last_error()
+    assert lib.acx_frame_fold(p, p, p, 1, 400, 2, 1024, 320, 0) != 0 and "reflect" in N.last_error()
     assert lib.acx_head(p, p, p, p, p, p, p, p, p, 1, 31, 7, 770, 527, N.ACX_BF16, 0) != 0 and "unsupported" in N.last_error()
     assert lib.acx_mlp_fused(p, p, p, p, p, p, p, 0, 96, 0) != 0 and "positive" in N.last_error()
     torch.cuda.synchronize()          # nothing above may have poisoned the context

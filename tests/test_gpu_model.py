@@ -397,12 +397,12 @@ def test_amplitude_contract_check_is_opt_in(models, monkeypatch):
 
 @pytest.mark.parametrize("env", [{"ACX_DWCONV": "simt"}, {"ACX_GP": "0"}, {"ACX_LN": "smem"}, {"ACX_DWCONV_TC_STAGES": "0"},
                                  {"ACX_DS_GP": "0"}, {"ACX_DS_FUSED": "0"}, {"ACX_DS_FUSED_C": "96,192,384"}, {"ACX_PDL": "0"},
-                                 {"ACX_PDL": "31"}])
+                                 {"ACX_PDL": "31"}, {"ACX_FRONTEND": "folded"}])
 def test_alternative_kernel_routes_agree(parity_sd, monkeypatch, env):
     """Every selectable route of the block -- CUDA-core depthwise conv + fused LayerNorm (round 1), tensor-core conv on
     row-major tensors, LayerNorm applied in shared memory instead of folded, planar layout in stage 0 only, transpose pass
     instead of a planar downsample GEMM, ln_patchify + GEMM instead of the implicit-GEMM downsample kernel (and that kernel at
-    all three widths), programmatic dependent launch off / on for every kernel family -- gives the same logits as the default route within the bf16-mode tolerance:
+    all three widths), programmatic dependent launch off / on for every kernel family, the front end on folded frames -- gives the same logits as the default route within the bf16-mode tolerance:
     the routes differ only in where roundings to bf16 happen."""
     wave = weights.make_waveforms(2, n_samples=64000, kind="tones", seed=3).to(DEV)
 
@@ -419,3 +419,23 @@ def test_alternative_kernel_routes_agree(parity_sd, monkeypatch, env):
     ref = O.forward(wave.cpu(), parity_sd)["clipwise_logits"]
     assert (alt - ref).abs().max().item() < TOL["bf16"]["logits"]
     assert (alt - base).abs().max().item() < TOL["bf16"]["logits"]
+
+
+def test_graph_replays_are_bit_identical_under_dependent_launch(models):
+    """Programmatic dependent launch lets every kernel's prologue start under the previous kernel's tail; a read or write
+    placed above `griddepcontrol.wait` by mistake would show up as run-to-run differences.  200 replays of the captured
+    graph at full batch width (64 clips: every persistent kernel has a tail), eager launches and a different batch in
+    between: each result equals the first one bit for bit."""
+    m = models["bf16"]
+    a = weights.make_waveforms(64, n_samples=64000, kind="tones", seed=11).to(DEV)
+    b = weights.make_waveforms(64, n_samples=64000, kind="noise", seed=12).to(DEV)
+    first_a = m(a)["clipwise_logits"].clone()
+    first_b = m(b)["clipwise_logits"].clone()
+    for i in range(100):
+        assert torch.equal(m(a)["clipwise_logits"], first_a), i
+        assert torch.equal(m(b)["clipwise_logits"], first_b), i
+    eng = m._get_engine()
+    eng.start_timing(None)                      # eager path: an event pair around every launch
+    eager = eng.run(a)["logits"].clone()
+    eng.stop_timing()
+    assert torch.equal(eager, first_a)
