@@ -219,8 +219,8 @@ class Engine:
         # which implementation of the two fusable pieces to run (both are libacx kernels)
         # front end: "fused" = the dense tensor-core kernel (default), "folded" = tensor-core kernel on folded frames (half the
         # DFT work, 0.355 vs 0.419 ms per 64 clips with its prep pass; needs the real-input symmetry of the loaded STFT rows.
-        # Opt-in: folding doubles the operand magnitude of correlated samples, and on real audio the log-mel error against the
-        # reference grows from p99 9e-4 dB to 2.6e-3 dB -- past the 1e-3 dB the parity tests assert), "simt" = fp32 CUDA cores
+        # Opt-in: on tonal / real audio the log-mel error against the reference grows from p99 9e-4 dB to 2.6e-3 dB -- past the
+        # 1e-3 dB the parity tests assert), "simt" = fp32 CUDA cores
         self.frontend = frontend or os.environ.get("ACX_FRONTEND", "fused" if precision == "bf16" else "simt")
         if self.frontend == "folded" and getattr(self.w, "dftf", None) is None:
             self.frontend = "fused"
