@@ -169,7 +169,27 @@ def extras_single_gpu(model, eng, device, peaks):
         "hbm_gbs": round(bytes_alg / (k_ms * 1e-3) / 1e9, 1), "hbm_frac": round(bytes_alg / (k_ms * 1e-3) / 1e9 / peaks["hbm"], 4),
         "tflops_dense_dft": round(flops / (k_ms * 1e-3) / 1e12, 1),
         "tensor_frac": round(flops / (k_ms * 1e-3) / 1e12 / peaks["tensor_sust"], 4)}
+    # the same config through the opt-in front end on folded frames (ACX_FRONTEND=folded): information only
+    try:
+        from audioset_convnext_inf_b200.engine import Engine
+        eng_f = Engine(model.state_dict(), device, precision="bf16", frontend="folded")
+        if eng_f.frontend == "folded":
+            eng_f.run(w512[:64], want=("logmel",))
+            eng_f.run(w512, want=("logmel",))
+            eng_f.start_timing(None)
+            eng_f.run(w512, want=("logmel",))
+            kf = {}
+            for tag, ms in eng_f.stop_timing():
+                kf[tag] = kf.get(tag, 0.0) + ms
+            kf_ms = sum(kf.values())
+            out["frontend_only"]["folded_opt_in"] = {
+                "clips_per_s_kernels": round(512 / (kf_ms * 1e-3), 1), "kernels_ms": {k: round(v, 4) for k, v in kf.items()},
+                "note": "real-input symmetry of the windowed DFT: half the MMAs; not the default (log-mel accuracy on tonal audio)"}
+        del eng_f
+    except Exception as e:  # noqa: BLE001 -- an information leg must not take the bench line down
+        out["frontend_only"]["folded_opt_in"] = {"error": str(e)[:200]}
     del w512
+    torch.cuda.empty_cache()
 
     # ---- configs[0] / configs[4]: batch-1 latency and the batch sweep (tagging + scene embedding) --------------------
     sweep = []
